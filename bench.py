@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- conditioning sets/sec of createU (U_NZentries) on B200, per the round contract.
+
+  python bench.py --gpus N --steps K --warmup W            own arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N ...            CPU arm: the restated reference
+                                                           (oracle/, OpenMP + LAPACK) on host cores
+
+Workload (BASELINE.json configs[1]): n = 1e6 uniform 2-D locations per GPU (weak scaling: n =
+N * 1e6, rows sharded by contiguous range, every rank holds all locations), m = 30, Matern
+nu = 1.5 closed form, standard Vecchia ('z') conditioning, per-location nuggets.  One step = one
+U_NZentries pass over the rank's rows.  `value` times the device-resident call (gpv_u_dev);
+`e2e` times the reference-facing call with host buffers (gpv_u_values_packed: nuggets H2D,
+packed U values D2H) -- the call createU() makes.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1_000_000
+M = 30
+D = 2
+NU = 1.5
+SIG2 = 1.0
+
+
+def flops_per_set(p, d, cov):
+    """every +,-,*,/,sqrt,exp,pow,K_nu counted as 1."""
+    c_cov = {"nu0.5": 3, "nu1.5": 6, "nu2.5": 9, "esqe": 8, "general": 4}[cov]
+    P = p * (p - 1) // 2
+    return p ** 3 / 3 + p ** 2 / 2 + p / 6 + p ** 2 + P * 3 * d + P * c_cov
+
+
+def bytes_per_set(p, d):
+    return p * 4 + p * d * 8 + 8 + p * 8 + p * 8
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_inputs(n_total, row_begin, row_end, device, use_gpu_nn=True):
+    from gpvecchia_b200 import harness as H
+    locs = H.make_locs(n_total, D, stream=2)
+    if use_gpu_nn:
+        revNN = H.ordered_nn_gpu(locs, M, row_begin, row_end, device=device)
+    else:
+        revNN = H.rev(H.ordered_nn_kdtree(locs, M, row_begin, row_end)).astype(np.int32)
+    # 'z' conditioning: neighbours on the response, self on the latent (vecchia_specify.R:189-190)
+    revCond = np.zeros(revNN.shape, dtype=np.int32)
+    revCond[revNN == 0] = np.iinfo(np.int32).min
+    revCond[:, -1] = 1
+    nuggets = H.make_nuggets(n_total, stream=2)
+    z = H.make_data(n_total, stream=2)
+    covparms = np.array([SIG2, H.default_range(n_total, D), NU])
+    return locs, revNN, revCond, nuggets, z, covparms
+
+
+def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None):
+    """Times the restated reference (oracle/: OpenMP schedule(static) + LAPACK dpotrf/dtrtrs) on a
+    bounded sample of the same workload's rows; returns (sets/s, threads, sample description)."""
+    import oracle as O
+    threads = threads or O.max_threads()
+    n_total = locs.shape[0]
+    nr = revNN_rows.shape[0]
+
+    def timed(nrows_s):
+        pr = O.RowsProblem(locs, revNN_rows[nr - nrows_s:], revCond_rows[nr - nrows_s:], row_begin + nr - nrows_s,
+                           nuggets, "matern", covparms)
+        t0 = time.perf_counter()
+        pr.run(threads)
+        return time.perf_counter() - t0
+    pilot = min(20000, nr)
+    timed(min(2000, nr))                      # thread-pool / page-fault warm-up
+    t_p = timed(pilot)
+    nrows_s = int(min(nr, max(pilot, pilot / t_p * target_s)))
+    t_s = timed(nrows_s)
+    lo = row_begin + nr - nrows_s
+    return nrows_s / t_s, threads, f"rows [{lo},{lo + nrows_s}) of the n={n_total} workload, {t_s:.1f} s"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--host-nn", action="store_true", help="build neighbour arrays with cKDTree on the host")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_total = args.n_per_gpu * world
+    p = M + 1
+    workload = f"cfg2: createU/U_NZentries, n={n_total} uniform 2-D locs ({args.n_per_gpu}/GPU), m={M}, Matern nu={NU}, 'z' conditioning"
+    config = dict(workload=workload, n=n_total, m=M, d=D, covmodel="matern", nu=NU, cond_yz="z",
+                  sharding=f"rows by contiguous range over {world} rank(s); locs replicated",
+                  l2="inputs+outputs per step (idx 124 MB + U 248 MB per 1e6 rows) exceed the 126 MB L2")
+
+    if args.impl == "reference":
+        # ---- CPU arm: the restated reference on this box's host cores, rank 0 only ----------------
+        if rank != 0:
+            return
+        import oracle as O
+        from gpvecchia_b200 import harness as H
+        n_s = min(n_total, 400_000)      # neighbour arrays for a bounded sample of the workload's rows
+        locs = H.make_locs(n_total, D, stream=2)
+        rb, re_ = n_total - n_s, n_total
+        try:
+            import gpvecchia_b200 as G
+            have_gpu = G.lib.gpv_device_count() > 0
+        except Exception:
+            have_gpu = False
+        if have_gpu and not args.host_nn:
+            revNN = H.ordered_nn_gpu(locs, M, rb, re_, device=0)
+        else:
+            revNN = H.rev(H.ordered_nn_kdtree(locs, M, rb, re_)).astype(np.int32)
+        revCond = np.zeros(revNN.shape, dtype=np.int32)
+        revCond[revNN == 0] = np.iinfo(np.int32).min
+        revCond[:, -1] = 1
+        nuggets = H.make_nuggets(n_total, stream=2)
+        covparms = np.array([SIG2, H.default_range(n_total, D), NU])
+        threads = O.max_threads()
+        # size one step to ~3 s of CPU work
+        rate0, _, _ = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, target_s=2.0)
+        rows_step = int(min(n_s, max(10000, rate0 * 3.0)))
+        pr = O.RowsProblem(locs, revNN[-rows_step:], revCond[-rows_step:], re_ - rows_step, nuggets, "matern", covparms)
+        for _ in range(args.warmup):
+            pr.run(threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pr.run(threads)
+        dt = time.perf_counter() - t0
+        value = rows_step * args.steps / dt
+        sample = (f"{rows_step} full rows per step (rows [{re_ - rows_step},{re_}) of the n={n_total} workload), "
+                  f"{threads} OpenMP threads, LAPACK={'openblas' if O.has_lapack() else 'textbook'}")
+        print(json.dumps({
+            "impl": "reference", "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": value, "unit": "sets/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ---- own arm --------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import gpvecchia_b200 as G
+    from gpvecchia_b200 import shard
+
+    if G.lib.gpv_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the gpvecchia_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    cuts = shard.uniform_cuts(n_total, world)
+    rb, re_ = int(cuts[rank]), int(cuts[rank + 1])
+    nrows = re_ - rb
+    t_gen = time.perf_counter()
+    locs, revNN, revCond, nuggets, z, covparms = make_inputs(n_total, rb, re_, local_rank, use_gpu_nn=not args.host_nn)
+    t_gen = time.perf_counter() - t_gen
+    obs = np.ones(n_total, dtype=np.int32)
+    h = G.UHandle(locs, revNN_full(revNN, rb, n_total), revCond_full(revCond, rb, n_total), obs=obs,
+                  row_begin=rb, row_end=re_, device=local_rank)
+
+    d_nug = torch.from_numpy(nuggets).to(dev)
+    d_out = torch.empty(nrows * p, dtype=torch.float64, device=dev)
+    d_z = torch.from_numpy(z).to(dev)
+    d_ll = torch.zeros(3, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        h.u_dev("matern", covparms, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = G.lib.gpv_launch_count()
+    ms_total = timed(step_dev, args.steps, args.warmup)
+    launches = int(G.lib.gpv_launch_count() - launches0) - 2 * args.warmup
+    clocks = sampler.stop()
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # kernel-only duration of the dominant kernel, CUDA events on the launching stream (library side)
+    kms = []
+    for _ in range(max(5, args.steps)):
+        step_dev()
+        kms.append(h.last_kernel_ms())
+    k_ms = float(np.mean(kms))
+    kname = h.last_kernel_name()
+
+    # ---- e2e: the reference-facing host-buffer call createU() makes --------------------------------
+    total_packed = h.packed_len
+    host_out = torch.empty(total_packed + 2 * n_total, dtype=torch.float64).pin_memory()
+    host_nug = torch.from_numpy(nuggets).pin_memory()
+    out_np, nug_np = host_out.numpy(), host_nug.numpy()
+
+    def step_e2e():
+        h.values_packed("matern", covparms, nug_np, nug_np, zentries_tail=True, out=out_np)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_steps / float(t_e2e.item())
+    h2d = 8 * n_total + 8 * n_total
+    d2h = 8 * (total_packed + 2 * n_total)
+
+    # ---- extras: loglik evals/sec (fused numerator, scalars out), other covariances ----------------
+    extras = {}
+    if not args.no_extras:
+        def step_ll():
+            h.u_dev("matern", covparms, d_nug.data_ptr(), None, d_zord=d_z.data_ptr(), d_loglik=d_ll.data_ptr(), stream=stream)
+        ms_ll = timed(step_ll, max(5, args.steps // 2), 3)
+        if world > 1:
+            shard.allreduce_loglik(d_ll)
+        extras["loglik_numerator_evals_per_s"] = (max(5, args.steps // 2)) / (ms_ll * 1e-3)
+        extras["loglik_numerator_sets_per_s"] = n_total * (max(5, args.steps // 2)) / (ms_ll * 1e-3)
+        per = {}
+        for tag, ct, cp in (("nu0.5", "matern", [SIG2, covparms[1], 0.5]), ("nu2.5", "matern", [SIG2, covparms[1], 2.5]),
+                            ("general_nu0.8", "matern", [SIG2, covparms[1], 0.8]),
+                            ("esqe", "esqe", [0.7, covparms[1], 0.3, covparms[1]])):
+            cpa = np.array(cp)
+            def fn(ct=ct, cpa=cpa):
+                h.u_dev(ct, cpa, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
+            ms = timed(fn, max(5, args.steps // 2), 3)
+            per[tag] = n_total * max(5, args.steps // 2) / (ms * 1e-3)
+        extras["sets_per_s_other_covariances"] = per
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    F = flops_per_set(p, D, "nu1.5")
+    B = bytes_per_set(p, D)
+    peak_tf = C.c_double(0)
+    G._lib.check(G.lib.gpv_measure_fp64_peak(local_rank, C.byref(peak_tf)))
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved_tf = F * nrows / (k_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf.value,
+        "peak_source": "DFMA micro-kernel measured in this run (gpv_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+        "flops_per_set": F, "sets_per_launch": nrows, "kernel_ms": k_ms,
+        "hbm": {"achieved": B * nrows / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": B * nrows / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_set": B, "peak_source": hbm_src},
+        "traffic": None,
+    }
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, cores, sample = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms)
+        cpu = {"value": rate, "unit": "sets/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "sets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "gpv_u_values_packed (createU's U_NZentries + packing, host buffers, pinned)"},
+            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+            "input_generation_s": t_gen,
+        }
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def revNN_full(revNN_rows, rb, n_total):
+    """gpv_create takes whole column-major arrays (as R passes them); place the shard's rows."""
+    if revNN_rows.shape[0] == n_total:
+        return revNN_rows
+    full = np.zeros((n_total, revNN_rows.shape[1]), dtype=np.int32)
+    full[rb:rb + revNN_rows.shape[0]] = revNN_rows
+    return full
+
+
+def revCond_full(revCond_rows, rb, n_total):
+    if revCond_rows.shape[0] == n_total:
+        return revCond_rows
+    full = np.full((n_total, revCond_rows.shape[1]), np.iinfo(np.int32).min, dtype=np.int32)
+    full[rb:rb + revCond_rows.shape[0]] = revCond_rows
+    return full
+
+
+if __name__ == "__main__":
+    main()

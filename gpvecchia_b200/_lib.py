@@ -1,0 +1,91 @@
+"""ctypes binding of libgpvecchia_b200.so (include/gpvecchia_b200.h).
+
+The shared library is the product; this module only declares its C signatures.  There is no
+Python/NumPy/PyTorch compute fallback: if the library is missing, import fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpvecchia_b200.so")
+
+GPV_OK = 0
+GPV_ERR_ARG, GPV_ERR_CUDA, GPV_ERR_COVTYPE, GPV_ERR_NOMEM, GPV_ERR_UNSUPPORTED = 1, 2, 3, 4, 5
+GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
+
+# every symbol include/gpvecchia_b200.h declares (tests check the .so exports all of them)
+EXPORTED = [
+    "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_destroy",
+    "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
+    "gpv_loglik_numerator", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_last_kernel_name",
+    "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
+    "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
+]
+
+
+class GpvError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"gpvecchia_b200 status {status}: {message}")
+        self.status = status
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`make -C gpvecchia_b200/csrc -j8` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "gpvecchia_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    cp = C.c_char_p
+    L.gpv_last_error.restype = cp
+    L.gpv_version.restype = cp
+    L.gpv_device_count.restype = i32
+    L.gpv_create.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, i64, i64, i32]
+    L.gpv_create.restype = i32
+    L.gpv_destroy.argtypes = [vp]
+    L.gpv_destroy.restype = None
+    L.gpv_set_revcond.argtypes = [vp, vp, i32]
+    L.gpv_set_revcond.restype = i32
+    L.gpv_u_nzentries.argtypes = [vp, cp, vp, i32, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_u_nzentries.restype = i32
+    L.gpv_packed_len.argtypes = [vp]
+    L.gpv_packed_len.restype = i64
+    L.gpv_u_values_packed.argtypes = [vp, cp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_u_values_packed.restype = i32
+    L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
+    L.gpv_loglik_numerator.restype = i32
+    L.gpv_u_dev.argtypes = [vp, cp, vp, i32, vp, vp, i32, vp, i64, vp, vp]
+    L.gpv_u_dev.restype = i32
+    L.gpv_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.gpv_last_kernel_ms.restype = i32
+    L.gpv_last_kernel_name.argtypes = [vp]
+    L.gpv_last_kernel_name.restype = cp
+    L.gpv_launch_count.restype = i64
+    L.gpv_U_NZentries.argtypes = [i32, i64, i64, i32, i32, vp, vp, vp, i32, vp, vp, cp, vp, i32, vp, vp,
+                                  C.POINTER(i64), C.POINTER(i64), i32]
+    L.gpv_U_NZentries.restype = i32
+    L.gpv_MaternFun.argtypes = [vp, i64, vp, vp, i32]
+    L.gpv_MaternFun.restype = i32
+    L.gpv_EsqeFun.argtypes = [vp, i64, vp, vp, i32]
+    L.gpv_EsqeFun.restype = i32
+    L.gpv_measure_fp64_peak.argtypes = [i32, C.POINTER(dbl)]
+    L.gpv_measure_fp64_peak.restype = i32
+    L.gpv_measure_copy_bw.argtypes = [i32, C.POINTER(dbl)]
+    L.gpv_measure_copy_bw.restype = i32
+    L.gpv_harness_ordered_nn.argtypes = [i64, i32, i32, vp, i64, i64, vp, i32]
+    L.gpv_harness_ordered_nn.restype = i32
+    # host-only self-test hooks of the general-nu machinery (single points; not a compute path)
+    L.gpv_selftest_matern_general_host.argtypes = [dbl, dbl, dbl]
+    L.gpv_selftest_matern_general_host.restype = dbl
+    L.gpv_selftest_table_eval_host.argtypes = [dbl, dbl, dbl, dbl, dbl]
+    L.gpv_selftest_table_eval_host.restype = dbl
+    return L
+
+
+lib = _load()
+
+
+def check(status):
+    if status != GPV_OK:
+        raise GpvError(status, lib.gpv_last_error().decode(errors="replace"))

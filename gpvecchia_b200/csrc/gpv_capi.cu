@@ -1,0 +1,930 @@
+// gpv_capi.cu -- C ABI of the B200-native U_NZentries path (include/gpvecchia_b200.h).
+//
+// Host side of the boundary that replaces _GPvecchia_U_NZentries (src/RcppExports.cpp:49-67) and
+// U_NZentries (src/U_NZentries.cpp:25-118).  No CPU compute path exists in this library: every
+// entry point that produces numbers launches the sm_100a kernels; without a CUDA device the calls
+// fail with GPV_ERR_CUDA.
+#define GPV_DEFINE_TABLE_BUILDER
+#include "../../include/gpvecchia_b200.h"
+#include "gpv_internal.h"
+#include "bessel_table.cuh"
+#include "rgamma_coeffs.h"
+
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cub/cub.cuh>
+
+using namespace gpv;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static gpv_status fail(gpv_status st, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return st;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(GPV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+extern "C" const char* gpv_last_error(void) { return g_err; }
+extern "C" const char* gpv_version(void) { return "gpvecchia_b200 0.1 (sm_100a)"; }
+extern "C" int gpv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int64_t gpv_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// kernel registry
+// ------------------------------------------------------------------------------------------------
+namespace gpv {
+static KernelEntry g_entries[64];
+static int g_nentries = 0;
+static std::once_flag g_reg_once;
+static void register_all() {
+  register_kernels_P4(g_entries, &g_nentries);
+  register_kernels_P8(g_entries, &g_nentries);
+  register_kernels_P11(g_entries, &g_nentries);
+  register_kernels_P16(g_entries, &g_nentries);
+  register_kernels_P21(g_entries, &g_nentries);
+  register_kernels_P26(g_entries, &g_nentries);
+  register_kernels_P31(g_entries, &g_nentries);
+  register_kernels_P32(g_entries, &g_nentries);
+}
+const KernelEntry* select_kernel(int p, int d) {
+  std::call_once(g_reg_once, register_all);
+  const int want_d = (d == 2 || d == 3) ? d : 0;
+  const KernelEntry* best = nullptr;
+  for (int i = 0; i < g_nentries; ++i) {
+    const KernelEntry& e = g_entries[i];
+    if (e.D != want_d || e.P < p) continue;
+    if (!best || e.P < best->P) best = &e;
+  }
+  return best;
+}
+}  // namespace gpv
+
+// ------------------------------------------------------------------------------------------------
+// preparation kernels (run once per handle)
+// ------------------------------------------------------------------------------------------------
+// column-major 1-based revNN (0 = missing) -> row-major 0-based (-1 = missing), shard rows only;
+// also per-row n0.
+__global__ void prep_nn_kernel(const int32_t* __restrict__ nn_cm, int64_t Nlocs, int p,
+                               int64_t row_begin, int64_t nrows, int32_t* __restrict__ nn_rm,
+                               int64_t* __restrict__ n0_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  int n0 = 0;
+  for (int j = 0; j < p; ++j) {
+    const int32_t v = nn_cm[(row_begin + r) + (int64_t)j * Nlocs];
+    nn_rm[r * p + j] = v - 1;           // 0 -> -1 (missing)
+    n0 += (v != 0);
+  }
+  n0_out[r] = n0;
+}
+template <typename T>
+__device__ inline bool cond_is_true(T v);
+template <>
+__device__ inline bool cond_is_true<int32_t>(int32_t v) { return v != 0 && v != INT_MIN; }
+template <>
+__device__ inline bool cond_is_true<double>(double v) { return v == 1.0; }
+// Only exact TRUE sets the bit.  With the f64 form the reference multiplies by (1 - revCond), so a
+// value other than 0/1 would scale the nugget; R can only pass 0/1/NA here (logical), NA rows are
+// never read (U_NZentries.cpp:47 reads the last n0 entries).
+template <typename T>
+__global__ void prep_cond_kernel(const T* __restrict__ cond_cm, int64_t Nlocs, int p,
+                                 int64_t row_begin, int64_t nrows, uint64_t* __restrict__ mask) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  uint64_t m = 0;
+  for (int j = 0; j < p; ++j)
+    if (cond_is_true<T>(cond_cm[(row_begin + r) + (int64_t)j * Nlocs])) m |= (1ull << j);
+  mask[r] = m;
+}
+__global__ void prep_locs_kernel(const double* __restrict__ locs_cm, int64_t Nlocs, int d,
+                                 double* __restrict__ locs_rm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nlocs) return;
+  for (int c = 0; c < d; ++c) locs_rm[i * d + c] = locs_cm[i + (int64_t)c * Nlocs];
+}
+__global__ void obs_flag_kernel(const int32_t* __restrict__ obs, int64_t Nlocs, int32_t* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Nlocs) flag[i] = (obs[i] != 0 && obs[i] != INT_MIN) ? 1 : 0;
+}
+__global__ void obs_rank_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ excl,
+                                int64_t Nlocs, int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Nlocs) rank[i] = flag[i] ? excl[i] : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-call elementwise kernels
+// ------------------------------------------------------------------------------------------------
+// Zentries (U_NZentries.cpp:110-115): Z[2i] = -1/sqrt(tau_i), Z[2i+1] = +1/sqrt(tau_i)
+__global__ void zentries_kernel(const double* __restrict__ tau, int64_t n, double* __restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = 1.0 / sqrt(tau[i]);
+  reinterpret_cast<double2*>(z)[i] = make_double2(-v, v);
+}
+// row-major (nrows x p) -> column-major, 32x32 tiles through shared memory
+__global__ void transpose_rm_to_cm_kernel(const double* __restrict__ in, int64_t nrows, int p,
+                                          double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    if (r < nrows && c < p) tile[i][threadIdx.x] = in[r * p + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (r < nrows && c < p) out[(int64_t)c * nrows + r] = tile[threadIdx.x][i];
+  }
+}
+// obs terms of the numerator: sum z_i^2 / tau_i and sum log tau_i (vecchia_likelihood.R:74-76 on
+// the Z columns of U), fixed-order per-block partials.
+__global__ void obs_terms_kernel(const double* __restrict__ zord, const double* __restrict__ tau,
+                                 int64_t n, double* __restrict__ partials) {
+  __shared__ double red[8][2];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double t = tau[i], z = zord[i];
+    a += z * z / t;
+    b += log(t);
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = a; red[warp][1] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s0 += red[w][0]; s1 += red[w][1]; }
+    partials[2 * blockIdx.x] = s0;
+    partials[2 * blockIdx.x + 1] = s1;
+  }
+}
+// out[0] = sum rows quad (+ obs quad), out[1] = -2 sum log x_self (+ sum log tau), out[2] = nfail.
+// Single thread, fixed order: run-to-run reproducible.
+__global__ void finalize_loglik_kernel(const double* __restrict__ row_partials, int nrow_blocks,
+                                       const double* __restrict__ obs_partials, int nobs_blocks,
+                                       const unsigned long long* __restrict__ nfail,
+                                       double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double q = 0.0, l = 0.0;
+  for (int i = 0; i < nrow_blocks; ++i) { q += row_partials[2 * i]; l += row_partials[2 * i + 1]; }
+  double logdet = -2.0 * l;
+  if (obs_partials != nullptr) {
+    double qo = 0.0, lo = 0.0;
+    for (int i = 0; i < nobs_blocks; ++i) { qo += obs_partials[2 * i]; lo += obs_partials[2 * i + 1]; }
+    q += qo;
+    logdet += lo;   // -2 * sum log(1/sqrt(tau)) = + sum log tau
+  }
+  out[0] = q;
+  out[1] = logdet;
+  out[2] = (double)(*nfail);
+}
+__global__ void reset_scalars_kernel(unsigned long long* nfail, long long* first_fail) {
+  *nfail = 0ull;
+  *first_fail = LLONG_MAX;
+}
+__global__ void cov_eval_kernel(const double* __restrict__ dist, int64_t len, UParams q,
+                                double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const double dd = dist[i];
+  double v;
+  if (dd == 0.0) v = q.c0;
+  else {
+    // the pair kernels work on the squared distance; here the argument is the distance itself
+    const double r2 = dd * dd;
+    switch (q.cov) {
+      case COV_EXP: v = q.c0 * exp(-dd * q.c1); break;
+      case COV_M15: { double t = dd * q.c1; v = q.c0 * (1.0 + t) * exp(-t); } break;
+      case COV_M25: { double t = dd * q.c1; v = q.c0 * exp(-t) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0); } break;
+      case COV_ESQE: v = cov_eval<COV_ESQE>(r2, q); break;
+      default: v = cov_eval<COV_GENERAL>(r2, q); break;
+    }
+  }
+  out[i] = v;
+}
+
+// measurement kernels --------------------------------------------------------------------------------
+__global__ void dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void copy_kernel(const double4* __restrict__ in, double4* __restrict__ out, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct gpv_handle {
+  int device = 0;
+  int64_t Nlocs = 0, row_begin = 0, row_end = 0, nrows = 0;
+  int p = 0, d = 0;
+  int64_t n_obs = 0;
+  bool have_obs = false;
+  int64_t packed_len = 0;
+  double w_max = 0.0;                 // squared diameter of the bounding box of locs
+  // resident, parameter-free
+  double* d_locs = nullptr;           // [Nlocs][d]
+  int32_t* d_nn = nullptr;            // [nrows][p]
+  uint64_t* d_cond = nullptr;         // [nrows]
+  int64_t* d_row_off = nullptr;       // [nrows]
+  int32_t* d_obsrank = nullptr;       // [Nlocs]
+  // per-call scratch (allocated lazily, reused)
+  double* d_nuggets = nullptr;        // [Nlocs]
+  double* d_tau = nullptr;            // [n_obs]
+  double* d_zord = nullptr;           // [n_obs]
+  double* d_out = nullptr;            // [nrows*p]
+  double* d_out2 = nullptr;           // [nrows*p] (column-major copy) or packed + Z
+  size_t out2_doubles = 0;
+  double* d_zent = nullptr;           // [2 n_obs]
+  double* d_partials = nullptr;       // [max_blocks*2]
+  double* d_obs_partials = nullptr;   // [kObsBlocks*2]
+  double* d_loglik = nullptr;         // [3]
+  unsigned long long* d_nfail = nullptr;
+  long long* d_first_fail = nullptr;
+  double* d_table = nullptr;          // general-nu coefficient table
+  int table_doubles = 0;
+  int max_blocks = 0;
+  const KernelEntry* entry = nullptr;
+  int blocks_per_sm = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool ev_valid = false;
+  const char* last_kernel = "";
+};
+static const int kObsBlocks = 296;
+
+static void free_handle(gpv_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
+  cudaFree(h->d_obsrank); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
+  cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
+  cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
+  cudaFree(h->d_first_fail); cudaFree(h->d_table);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+template <typename T>
+static gpv_status upload_cond(gpv_handle* h, const void* host) {
+  T* tmp = nullptr;
+  const size_t bytes = sizeof(T) * (size_t)h->Nlocs * h->p;
+  CUDA_TRY(cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    prep_cond_kernel<T><<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, h->Nlocs, h->p,
+                                                                        h->row_begin, h->nrows, h->d_cond);
+    g_launches++;
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(GPV_ERR_CUDA, "revCond upload failed: %s", cudaGetErrorString(e));
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_set_revcond(gpv_handle* h, const void* revCond, gpv_cond_type cond_type) {
+  if (!h || !revCond) return fail(GPV_ERR_ARG, "gpv_set_revcond: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->nrows == 0) return GPV_OK;
+  if (cond_type == GPV_COND_RLOGICAL_I32) return upload_cond<int32_t>(h, revCond);
+  if (cond_type == GPV_COND_F64) return upload_cond<double>(h, revCond);
+  return fail(GPV_ERR_ARG, "gpv_set_revcond: unknown cond_type %d", (int)cond_type);
+}
+
+extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                                 const int32_t* revNNarray, const void* revCond,
+                                 gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
+                                 int64_t row_end, int device) {
+  if (!out) return fail(GPV_ERR_ARG, "gpv_create: out is null");
+  *out = nullptr;
+  if (!locs || !revNNarray || !revCond) return fail(GPV_ERR_ARG, "gpv_create: null input array");
+  if (Nlocs <= 0 || p <= 0 || d <= 0) return fail(GPV_ERR_ARG, "gpv_create: bad shape N=%lld p=%d d=%d", (long long)Nlocs, p, d);
+  if (p > GPV_MAX_P) return fail(GPV_ERR_ARG, "gpv_create: p=%d exceeds GPV_MAX_P=%d", p, GPV_MAX_P);
+  if (d > GPV_MAX_D) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: d=%d exceeds GPV_MAX_D=%d", d, GPV_MAX_D);
+  if (row_begin < 0 || row_end > Nlocs || row_begin > row_end)
+    return fail(GPV_ERR_ARG, "gpv_create: bad row range [%lld,%lld)", (long long)row_begin, (long long)row_end);
+  if (Nlocs > (int64_t)INT32_MAX) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: Nlocs exceeds int32 ids");
+  const KernelEntry* entry = select_kernel(p, d);
+  if (!entry) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: no kernel instantiated for p=%d (m=%d), d=%d", p, p - 1, d);
+
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(GPV_ERR_ARG, "gpv_create: device %d of %d", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+
+  gpv_handle* h = new (std::nothrow) gpv_handle();
+  if (!h) return fail(GPV_ERR_NOMEM, "gpv_create: host allocation failed");
+  h->device = device; h->Nlocs = Nlocs; h->p = p; h->d = d;
+  h->row_begin = row_begin; h->row_end = row_end; h->nrows = row_end - row_begin;
+  h->entry = entry;
+#define H_TRY(expr)                                                                                 \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      gpv_status _s = fail(GPV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                           __FILE__, __LINE__);                                                     \
+      free_handle(h);                                                                               \
+      return _s;                                                                                    \
+    }                                                                                               \
+  } while (0)
+
+  cudaDeviceProp prop;
+  H_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  H_TRY(cudaEventCreate(&h->ev_start));
+  H_TRY(cudaEventCreate(&h->ev_stop));
+  H_TRY(cudaFuncSetAttribute((const void*)entry->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             entry->smem_bytes));
+  H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, (const void*)entry->kernel,
+                                                      kWarpsPerBlock * 32, entry->smem_bytes));
+  if (h->blocks_per_sm < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry->name); }
+  h->max_blocks = h->num_sms * h->blocks_per_sm;
+
+  const size_t nr = (size_t)(h->nrows > 0 ? h->nrows : 1);
+  H_TRY(cudaMalloc(&h->d_locs, sizeof(double) * (size_t)Nlocs * d));
+  H_TRY(cudaMalloc(&h->d_nn, sizeof(int32_t) * nr * p));
+  H_TRY(cudaMalloc(&h->d_cond, sizeof(uint64_t) * nr));
+  H_TRY(cudaMalloc(&h->d_row_off, sizeof(int64_t) * nr));
+  H_TRY(cudaMalloc(&h->d_nuggets, sizeof(double) * (size_t)Nlocs));
+  H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * (size_t)h->max_blocks));
+  H_TRY(cudaMalloc(&h->d_obs_partials, sizeof(double) * 2 * kObsBlocks));
+  H_TRY(cudaMalloc(&h->d_loglik, sizeof(double) * 3));
+  H_TRY(cudaMalloc(&h->d_nfail, sizeof(unsigned long long)));
+  H_TRY(cudaMalloc(&h->d_first_fail, sizeof(long long)));
+
+  // locs: upload column-major, transpose on device; bounding box on the host copy (once)
+  {
+    double* tmp = nullptr;
+    H_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)Nlocs * d));
+    cudaError_t e = cudaMemcpyAsync(tmp, locs, sizeof(double) * (size_t)Nlocs * d, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      prep_locs_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(tmp, Nlocs, d, h->d_locs);
+      g_launches++;
+      e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(tmp);
+    H_TRY(e);
+    double w = 0.0;
+    for (int c = 0; c < d; ++c) {
+      double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+      const double* col = locs + (size_t)c * Nlocs;
+      for (int64_t i = 0; i < Nlocs; ++i) { mn = col[i] < mn ? col[i] : mn; mx = col[i] > mx ? col[i] : mx; }
+      w += (mx - mn) * (mx - mn);
+    }
+    h->w_max = w;
+  }
+  // neighbour ids: upload column-major, transpose + rebase on device, packed offsets by scan
+  if (h->nrows > 0) {
+    int32_t* tmp = nullptr;
+    int64_t* n0 = nullptr;
+    H_TRY(cudaMalloc(&tmp, sizeof(int32_t) * (size_t)Nlocs * p));
+    cudaError_t e = cudaMalloc(&n0, sizeof(int64_t) * nr);
+    void* scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, revNNarray, sizeof(int32_t) * (size_t)Nlocs * p, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      prep_nn_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, Nlocs, p, row_begin, h->nrows, h->d_nn, n0);
+      g_launches++;
+      e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, n0, h->d_row_off, (int)h->nrows, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 1);
+    if (e == cudaSuccess) {
+      e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, n0, h->d_row_off, (int)h->nrows, h->stream);
+      g_launches++;
+    }
+    int64_t last_off = 0, last_n0 = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_off, h->d_row_off + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_n0, n0 + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp); cudaFree(n0); cudaFree(scan_tmp);
+    H_TRY(e);
+    h->packed_len = last_off + last_n0;
+  }
+  // obs -> rank among observed (index into zord)
+  if (obs != nullptr) {
+    int32_t *tmp = nullptr, *flag = nullptr, *excl = nullptr;
+    void* scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    H_TRY(cudaMalloc(&h->d_obsrank, sizeof(int32_t) * (size_t)Nlocs));
+    cudaError_t e = cudaMalloc(&tmp, sizeof(int32_t) * (size_t)Nlocs);
+    if (e == cudaSuccess) e = cudaMalloc(&flag, sizeof(int32_t) * (size_t)Nlocs);
+    if (e == cudaSuccess) e = cudaMalloc(&excl, sizeof(int32_t) * (size_t)Nlocs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, obs, sizeof(int32_t) * (size_t)Nlocs, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      obs_flag_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(tmp, Nlocs, flag);
+      g_launches++;
+      e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flag, excl, (int)Nlocs, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 1);
+    if (e == cudaSuccess) {
+      e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flag, excl, (int)Nlocs, h->stream);
+      g_launches++;
+    }
+    int32_t last_e = 0, last_f = 0;
+    if (e == cudaSuccess) {
+      obs_rank_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(flag, excl, Nlocs, h->d_obsrank);
+      g_launches++;
+      e = cudaMemcpyAsync(&last_e, excl + (Nlocs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_f, flag + (Nlocs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp); cudaFree(flag); cudaFree(excl); cudaFree(scan_tmp);
+    H_TRY(e);
+    h->n_obs = (int64_t)last_e + last_f;
+    h->have_obs = true;
+  }
+  *out = h;
+  gpv_status st = gpv_set_revcond(h, revCond, cond_type);
+  if (st != GPV_OK) { free_handle(h); *out = nullptr; return st; }
+  return GPV_OK;
+#undef H_TRY
+}
+
+extern "C" void gpv_destroy(gpv_handle* h) { free_handle(h); }
+extern "C" int64_t gpv_packed_len(const gpv_handle* h) { return h ? h->packed_len : 0; }
+extern "C" const char* gpv_last_kernel_name(const gpv_handle* h) { return h ? h->last_kernel : ""; }
+
+extern "C" gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms) {
+  if (!h || !ms) return fail(GPV_ERR_ARG, "gpv_last_kernel_ms: null argument");
+  if (!h->ev_valid) return fail(GPV_ERR_ARG, "gpv_last_kernel_ms: no launch recorded yet");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->ev_stop));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+  return GPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// covariance set-up (per call)
+// ------------------------------------------------------------------------------------------------
+static void nu_constants(double nu, double sig2, CovTable* t) {
+  // Temme's auxiliary functions for |mu| <= 1/2 from the Taylor series of 1/Gamma(1+x)
+  const int nl = (int)(nu + 0.5);
+  const double xmu = nu - nl;
+  const double m2 = xmu * xmu;
+  double g1 = 0.0, g2 = 0.0, pl = 0.0, mi = 0.0;
+  // gam2 = sum_{k even} c_k mu^k ; gam1 = -sum_{k odd} c_k mu^(k-1)
+  for (int k = GPV_RGAMMA_NCOEF - 1; k >= 0; --k) {
+    pl = pl * xmu + kRGammaTaylor[k];
+    mi = mi * (-xmu) + kRGammaTaylor[k];
+  }
+  for (int k = ((GPV_RGAMMA_NCOEF - 1) / 2) * 2; k >= 0; k -= 2) g2 = g2 * m2 + kRGammaTaylor[k];
+  for (int k = ((GPV_RGAMMA_NCOEF - 2) / 2) * 2 + 1; k >= 1; k -= 2) g1 = g1 * m2 + kRGammaTaylor[k];
+  t->nu = nu; t->nl = nl; t->xmu = xmu;
+  t->gam1 = -g1; t->gam2 = g2; t->gampl = pl; t->gammi = mi;
+  t->normcon = sig2 / (std::pow(2.0, nu - 1.0) * std::tgamma(nu));   // Matern.cpp:73
+}
+
+struct CovSetup {
+  UParams q;
+  bool needs_table = false;
+};
+
+static gpv_status setup_cov(const char* covType, const double* covparms, int ncov, double w_max,
+                            CovSetup* cs) {
+  if (!covType || !covparms) return fail(GPV_ERR_ARG, "covType/covparms is null");
+  UParams& q = cs->q;
+  std::memset(&q, 0, sizeof(q));
+  if (std::strcmp(covType, "matern") == 0) {
+    if (ncov < 3) return fail(GPV_ERR_ARG, "matern needs covparms = (sig2, range, smooth)");
+    const double sig2 = covparms[0], range = covparms[1], nu = covparms[2];
+    q.c0 = sig2;
+    q.inv_range = 1.0 / range;
+    if (nu == 0.5) { q.cov = COV_EXP; q.c1 = 1.0 / range; }                       // Matern.cpp:32
+    else if (nu == 1.5) { q.cov = COV_M15; q.c1 = std::sqrt(3.0) / range; }       // :43
+    else if (nu == 2.5) { q.cov = COV_M25; q.c1 = std::sqrt(5.0) / range; }       // :58
+    else {                                                                        // :72
+      if (!(nu > 0.0) || !std::isfinite(nu)) return fail(GPV_ERR_ARG, "matern smoothness must be positive and finite (got %g)", nu);
+      q.cov = COV_GENERAL;
+      cs->needs_table = true;
+      CovTable& t = q.tab;
+      nu_constants(nu, sig2, &t);
+      // table range: the top kTabOctaves octaves of w below the squared bounding-box diagonal
+      double wmax = (w_max > 0.0 && std::isfinite(w_max)) ? w_max : 1.0;
+      const int code_hi = hi32_of(wmax) >> (20 - kTabSubBits);
+      int nint = kTabOctaves * kTabSub;
+      int idx0 = code_hi - nint + 1;
+      const int min_code = 1 << kTabSubBits;            // smallest normal exponent
+      if (idx0 < min_code) { nint -= (min_code - idx0); idx0 = min_code; }
+      t.idx0 = idx0; t.nint = nint; t.sub_bits = kTabSubBits; t.deg = kTabDeg;
+      const double ws = (kTabSSplit * range) * (kTabSSplit * range);
+      const int code_split = hi32_of(ws) >> (20 - kTabSubBits);
+      t.w_split = from_hilo(code_split << (20 - kTabSubBits), 0);
+    }
+  } else if (std::strcmp(covType, "esqe") == 0) {
+    if (ncov < 4) return fail(GPV_ERR_ARG, "esqe needs covparms = (sig2_1, r1, sig2_2, r2)");
+    q.cov = COV_ESQE;
+    q.c0 = covparms[0] + covparms[2];            // Esqe.cpp:29-30
+    q.c4 = covparms[0];
+    q.c1 = 1.0 / covparms[1];
+    q.c2 = covparms[2];
+    q.c3 = 1.0 / (covparms[3] * covparms[3]);
+  } else {
+    return fail(GPV_ERR_COVTYPE, "%s covariance is not implemented", covType);   // U_NZentries.cpp:27-29
+  }
+  return GPV_OK;
+}
+
+static gpv_status ensure_table(gpv_handle* h, CovSetup* cs, cudaStream_t st) {
+  if (!cs->needs_table) return GPV_OK;
+  CovTable& t = cs->q.tab;
+  const int need = (kTabDeg + 1) * t.nint;
+  if (need > h->table_doubles) {
+    if (h->d_table) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(h->d_table); h->d_table = nullptr; }
+    CUDA_TRY(cudaMalloc(&h->d_table, sizeof(double) * (size_t)need));
+    h->table_doubles = need;
+  }
+  t.coef = h->d_table;
+  build_cov_table_kernel<<<t.nint, 32, 0, st>>>(t, cs->q.inv_range, h->d_table);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch of the set kernel
+// ------------------------------------------------------------------------------------------------
+static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nuggets, double* d_out,
+                              int packed, const double* d_zord, int64_t skip_rows, bool want_loglik,
+                              cudaStream_t st, int* nblocks_out) {
+  UParams& q = cs->q;
+  q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
+  q.locs = h->d_locs; q.nn = h->d_nn; q.cond = h->d_cond; q.nuggets = d_nuggets;
+  q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
+  q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
+  q.partials = want_loglik ? h->d_partials : nullptr;
+  q.nfail = h->d_nfail; q.first_fail = h->d_first_fail;
+  const KernelEntry* e = h->entry;
+  const int sets_per_block = kWarpsPerBlock * (32 / e->G);
+  int64_t want = (h->nrows + sets_per_block - 1) / sets_per_block;
+  int blocks = (int)(want < (int64_t)h->max_blocks ? want : (int64_t)h->max_blocks);
+  if (blocks < 1) blocks = 1;
+  reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
+  g_launches++;
+  CUDA_TRY(cudaEventRecord(h->ev_start, st));
+  e->kernel<<<blocks, kWarpsPerBlock * 32, e->smem_bytes, st>>>(q);
+  g_launches++;
+  CUDA_TRY(cudaEventRecord(h->ev_stop, st));
+  CUDA_TRY(cudaGetLastError());
+  h->ev_valid = true;
+  h->last_kernel = e->name;
+  if (nblocks_out) *nblocks_out = blocks;
+  return GPV_OK;
+}
+
+static gpv_status ensure(double** ptr, size_t doubles) {
+  if (*ptr) return GPV_OK;
+  CUDA_TRY(cudaMalloc(ptr, sizeof(double) * (doubles ? doubles : 1)));
+  return GPV_OK;
+}
+
+static gpv_status read_fail_info(gpv_handle* h, int64_t* nfail, int64_t* first_fail) {
+  unsigned long long nf = 0;
+  long long ff = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nf, h->d_nfail, sizeof(nf), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(&ff, h->d_first_fail, sizeof(ff), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (nfail) *nfail = (int64_t)nf;
+  if (first_fail) *first_fail = (nf == 0) ? -1 : (int64_t)ff;
+  return GPV_OK;
+}
+
+static gpv_status run_zentries(gpv_handle* h, const double* nuggets_obsord, int64_t n) {
+  if (n <= 0) return GPV_OK;
+  if (h->n_obs != 0 && h->have_obs && n != h->n_obs)
+    return fail(GPV_ERR_ARG, "n=%lld does not match sum(obs)=%lld", (long long)n, (long long)h->n_obs);
+  if (!h->d_tau || !h->d_zent) {
+    cudaFree(h->d_tau); cudaFree(h->d_zent); h->d_tau = nullptr; h->d_zent = nullptr;
+  }
+  gpv_status s = ensure(&h->d_tau, (size_t)n); if (s) return s;
+  s = ensure(&h->d_zent, 2 * (size_t)n); if (s) return s;
+  CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  zentries_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_tau, n, h->d_zent);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double* covparms, int ncov,
+                                const double* d_nuggets, double* d_out, int packed,
+                                const double* d_zord, int64_t skip_rows, double* d_loglik,
+                                void* stream) {
+  if (!h || !d_nuggets) return fail(GPV_ERR_ARG, "gpv_u_dev: null argument");
+  if (d_loglik && (!d_zord || !h->have_obs)) return fail(GPV_ERR_ARG, "gpv_u_dev: likelihood needs d_zord and obs at create time");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  CovSetup cs;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  s = ensure_table(h, &cs, st); if (s) return s;
+  int nblocks = 0;
+  s = launch_sets(h, &cs, d_nuggets, d_out, packed, d_zord, skip_rows, d_loglik != nullptr, st, &nblocks);
+  if (s) return s;
+  if (d_loglik) {
+    finalize_loglik_kernel<<<1, 32, 0, st>>>(h->d_partials, nblocks, nullptr, 0, h->d_nfail, d_loglik);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return GPV_OK;
+}
+
+// shared body of gpv_u_nzentries / gpv_u_values_packed
+static gpv_status u_host_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
+                                const double* nuggets, const double* nuggets_obsord, int64_t n,
+                                int packed, int ztail, double* out, double* zout, int64_t* nfail,
+                                int64_t* first_fail) {
+  if (!h || !nuggets || !out) return fail(GPV_ERR_ARG, "null argument");
+  if (n > 0 && !nuggets_obsord) return fail(GPV_ERR_ARG, "nuggets_obsord is null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CovSetup cs;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  s = ensure_table(h, &cs, h->stream); if (s) return s;
+  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+  const size_t full = (size_t)h->nrows * h->p;
+  s = ensure(&h->d_out, full); if (s) return s;
+  if (h->nrows > 0) {
+    s = launch_sets(h, &cs, h->d_nuggets, h->d_out, packed, nullptr, 0, false, h->stream, nullptr);
+    if (s) return s;
+  } else {
+    reset_scalars_kernel<<<1, 1, 0, h->stream>>>(h->d_nfail, h->d_first_fail);
+    g_launches++;
+  }
+  const bool want_z = (n > 0) && (zout != nullptr || ztail);
+  if (want_z) { s = run_zentries(h, nuggets_obsord, n); if (s) return s; }
+  if (packed) {
+    if (h->packed_len > 0)
+      CUDA_TRY(cudaMemcpyAsync(out, h->d_out, sizeof(double) * (size_t)h->packed_len, cudaMemcpyDeviceToHost, h->stream));
+    if (ztail && n > 0)
+      CUDA_TRY(cudaMemcpyAsync(out + h->packed_len, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  } else if (h->nrows > 0) {
+    if (h->out2_doubles < full) {
+      cudaFree(h->d_out2); h->d_out2 = nullptr; h->out2_doubles = 0;
+      CUDA_TRY(cudaMalloc(&h->d_out2, sizeof(double) * full));
+      h->out2_doubles = full;
+    }
+    dim3 grid(grid_for(h->nrows, 32), (h->p + 31) / 32), block(32, 8);
+    transpose_rm_to_cm_kernel<<<grid, block, 0, h->stream>>>(h->d_out, h->nrows, h->p, h->d_out2);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_out2, sizeof(double) * full, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (!packed && zout && n > 0)
+    CUDA_TRY(cudaMemcpyAsync(zout, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  return read_fail_info(h, nfail, first_fail);
+}
+
+extern "C" gpv_status gpv_u_nzentries(gpv_handle* h, const char* covType, const double* covparms,
+                                      int ncov, const double* nuggets, const double* nuggets_obsord,
+                                      int64_t n, double* Lentries, double* Zentries, int64_t* nfail,
+                                      int64_t* first_fail) {
+  return u_host_common(h, covType, covparms, ncov, nuggets, nuggets_obsord, n, 0, 0, Lentries,
+                       Zentries, nfail, first_fail);
+}
+
+extern "C" gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, const double* covparms,
+                                          int ncov, const double* nuggets,
+                                          const double* nuggets_obsord, int64_t n, int zentries_tail,
+                                          double* out, int64_t* nfail, int64_t* first_fail) {
+  return u_host_common(h, covType, covparms, ncov, nuggets, nuggets_obsord, n, 1, zentries_tail, out,
+                       nullptr, nfail, first_fail);
+}
+
+extern "C" gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, const double* covparms,
+                                           int ncov, const double* nuggets,
+                                           const double* nuggets_obsord, const double* zord, int64_t n,
+                                           int64_t skip_rows, int include_obs_terms, double out[3]) {
+  if (!h || !nuggets || !nuggets_obsord || !zord || !out) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: null argument");
+  if (!h->have_obs) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: handle was created without obs");
+  if (n != h->n_obs) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: n=%lld but sum(obs)=%lld", (long long)n, (long long)h->n_obs);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CovSetup cs;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  s = ensure_table(h, &cs, h->stream); if (s) return s;
+  s = ensure(&h->d_tau, (size_t)n); if (s) return s;
+  s = ensure(&h->d_zord, (size_t)n); if (s) return s;
+  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_zord, zord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  int nblocks = 0;
+  if (h->nrows > 0) {
+    s = launch_sets(h, &cs, h->d_nuggets, nullptr, 0, h->d_zord, skip_rows, true, h->stream, &nblocks);
+    if (s) return s;
+  } else {
+    reset_scalars_kernel<<<1, 1, 0, h->stream>>>(h->d_nfail, h->d_first_fail);
+    g_launches++;
+  }
+  const bool obs_terms = (include_obs_terms < 0) ? (h->row_begin == 0) : (include_obs_terms != 0);
+  if (obs_terms && n > 0) {
+    obs_terms_kernel<<<kObsBlocks, 256, 0, h->stream>>>(h->d_zord, h->d_tau, n, h->d_obs_partials);
+    g_launches++;
+  }
+  finalize_loglik_kernel<<<1, 32, 0, h->stream>>>(h->d_partials, nblocks,
+                                                  (obs_terms && n > 0) ? h->d_obs_partials : nullptr,
+                                                  kObsBlocks, h->d_nfail, h->d_loglik);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_loglik, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_U_NZentries(int Ncores, int64_t n, int64_t Nlocs, int p, int d,
+                                      const double* locs, const int32_t* revNNarray,
+                                      const void* revCond, gpv_cond_type cond_type,
+                                      const double* nuggets, const double* nuggets_obsord,
+                                      const char* covType, const double* covparms, int ncov,
+                                      double* Lentries, double* Zentries, int64_t* nfail,
+                                      int64_t* first_fail, int device) {
+  (void)Ncores;   // the reference's OpenMP team size has no meaning here
+  // validate covType before touching the device, like the message at U_NZentries.cpp:27-29
+  CovSetup probe;
+  gpv_status s = setup_cov(covType, covparms, ncov, 1.0, &probe); if (s) return s;
+  gpv_handle* h = nullptr;
+  s = gpv_create(&h, Nlocs, p, d, locs, revNNarray, revCond, cond_type, nullptr, 0, Nlocs, device);
+  if (s) return s;
+  s = gpv_u_nzentries(h, covType, covparms, ncov, nuggets, nuggets_obsord, n, Lentries, Zentries, nfail, first_fail);
+  gpv_destroy(h);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaternFun / EsqeFun
+// ------------------------------------------------------------------------------------------------
+static gpv_status cov_fun_common(const char* covType, const double* dist, int64_t len,
+                                 const double* covparms, int ncov, double* out, int device) {
+  if (!dist || !out || len < 0) return fail(GPV_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  double wmax = 0.0;
+  for (int64_t i = 0; i < len; ++i) { const double w = dist[i] * dist[i]; if (std::isfinite(w) && w > wmax) wmax = w; }
+  CovSetup cs;
+  gpv_status s = setup_cov(covType, covparms, ncov, wmax, &cs); if (s) return s;
+  if (len == 0) return GPV_OK;
+  double *d_in = nullptr, *d_out = nullptr, *d_tab = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, sizeof(double) * (size_t)len);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * (size_t)len);
+  if (e == cudaSuccess && cs.needs_table) {
+    e = cudaMalloc(&d_tab, sizeof(double) * (size_t)(kTabDeg + 1) * cs.q.tab.nint);
+    if (e == cudaSuccess) {
+      cs.q.tab.coef = d_tab;
+      build_cov_table_kernel<<<cs.q.tab.nint, 32>>>(cs.q.tab, cs.q.inv_range, d_tab);
+      g_launches++;
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, dist, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    cov_eval_kernel<<<grid_for(len, 256), 256>>>(d_in, len, cs.q, d_out);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_tab);
+  if (e != cudaSuccess) return fail(GPV_ERR_CUDA, "covariance evaluation failed: %s", cudaGetErrorString(e));
+  return GPV_OK;
+}
+extern "C" gpv_status gpv_MaternFun(const double* dist, int64_t len, const double* covparms,
+                                    double* out, int device) {
+  return cov_fun_common("matern", dist, len, covparms, 3, out, device);
+}
+extern "C" gpv_status gpv_EsqeFun(const double* dist, int64_t len, const double* covparms, double* out,
+                                  int device) {
+  return cov_fun_common("esqe", dist, len, covparms, 4, out, device);
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" gpv_status gpv_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(GPV_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_TRY(cudaEventRecord(a));
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+    g_launches++;
+    CUDA_TRY(cudaEventRecord(b));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return GPV_OK;
+}
+extern "C" gpv_status gpv_measure_copy_bw(int device, double* gbs) {
+  if (!gbs) return fail(GPV_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  const int64_t n4 = (int64_t)1 << 26;   // 2 GiB per buffer (64 Mi double4)
+  double4 *a = nullptr, *b = nullptr;
+  CUDA_TRY(cudaMalloc(&a, sizeof(double4) * (size_t)n4));
+  if (cudaMalloc(&b, sizeof(double4) * (size_t)n4) != cudaSuccess) { cudaFree(a); return fail(GPV_ERR_CUDA, "copy buffer allocation failed"); }
+  cudaMemset(a, 0, sizeof(double4) * (size_t)n4);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    copy_kernel<<<148 * 16, 512>>>(a, b, n4);
+    g_launches++;
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+  *gbs = 2.0 * sizeof(double4) * (double)n4 / (best * 1e-3) / 1e9;
+  return GPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-only self-test hooks for the general-nu machinery (NOT a compute path: they evaluate the
+// same __host__ __device__ routines on single points so CPU-only CI can validate the algorithm).
+// ------------------------------------------------------------------------------------------------
+extern "C" double gpv_selftest_matern_general_host(double s, double sig2, double nu) {
+  CovTable t;
+  std::memset(&t, 0, sizeof(t));
+  nu_constants(nu, sig2, &t);
+  return matern_general_scaled(s, t, false);
+}
+// Builds the table on the host with the same fit routine and evaluates it at squared distance w.
+// Returns the tabulated covariance (including the exp(-s) factor where the table is scaled).
+extern "C" double gpv_selftest_table_eval_host(double w, double sig2, double range, double nu,
+                                               double w_max) {
+  CovSetup cs;
+  const double cp[3] = {sig2, range, nu};
+  if (setup_cov("matern", cp, 3, w_max, &cs) != GPV_OK || !cs.needs_table) return NAN;
+  const CovTable& t = cs.q.tab;
+  const int idx = (hi32_of(w) >> (20 - kTabSubBits)) - t.idx0;
+  if (idx < 0 || idx >= t.nint) return matern_general_scaled(std::sqrt(w) * cs.q.inv_range, t, false);
+  constexpr int n = kTabDeg + 1;
+  double w_lo, w_mid, w_half, f[n], mono[n];
+  table_interval(idx, t.idx0, &w_lo, &w_mid, &w_half);
+  const double kPi = 3.141592653589793238462643383279502884;
+  for (int i = 0; i < n; ++i) {
+    const double wn = w_mid + w_half * std::cos(kPi * (i + 0.5) / n);
+    f[i] = matern_general_scaled(std::sqrt(wn) * cs.q.inv_range, t, w_lo >= t.w_split);
+  }
+  cheb_fit_to_monomial(f, 1.0 / (double)(2 * kTabSub), mono);
+  const int hi = hi32_of(w), lo = lo32_of(w);
+  const double m = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo);
+  const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
+  const double mc = from_hilo((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
+  const double v = m - mc;
+  double acc = mono[kTabDeg];
+  for (int k = kTabDeg - 1; k >= 0; --k) acc = std::fma(acc, v, mono[k]);
+  if (w >= t.w_split) acc *= std::exp(-std::sqrt(w) * cs.q.inv_range);
+  return acc;
+}

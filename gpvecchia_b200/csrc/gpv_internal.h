@@ -1,0 +1,30 @@
+// gpv_internal.h -- shared declarations of the library's translation units (not installed).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "u_kernels.cuh"
+
+namespace gpv {
+
+// One entry per compiled instantiation of u_sets_kernel<G,P,D>.
+struct KernelEntry {
+  int G, P, D;                                 // D = 0: runtime d <= GPV_MAX_D
+  const char* name;
+  void (*kernel)(const UParams);
+  int smem_bytes;
+};
+
+// Picks the smallest instantiated P >= p for dimension d; nullptr if none.
+const KernelEntry* select_kernel(int p, int d);
+
+// Registration helpers implemented in u_inst_*.cu (one file per P so make -j parallelises nvcc).
+void register_kernels_P4(KernelEntry* out, int* n);
+void register_kernels_P8(KernelEntry* out, int* n);
+void register_kernels_P11(KernelEntry* out, int* n);
+void register_kernels_P16(KernelEntry* out, int* n);
+void register_kernels_P21(KernelEntry* out, int* n);
+void register_kernels_P26(KernelEntry* out, int* n);
+void register_kernels_P31(KernelEntry* out, int* n);
+void register_kernels_P32(KernelEntry* out, int* n);
+
+}  // namespace gpv

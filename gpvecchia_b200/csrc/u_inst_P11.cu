@@ -1,0 +1,3 @@
+#define GPV_INST_P 11
+#define GPV_INST_G 16
+#include "u_inst.inc"

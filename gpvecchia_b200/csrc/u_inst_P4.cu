@@ -1,0 +1,3 @@
+#define GPV_INST_P 4
+#define GPV_INST_G 8
+#include "u_inst.inc"

@@ -1,0 +1,155 @@
+/* gpvecchia_b200.h -- C ABI of the B200-native U_NZentries / likelihood-numerator path.
+ *
+ * Drop-in boundary: these entry points are what the reference's `.Call` glue for this path
+ * binds.  Reference interface replaced (GPvecchia 0.1.8):
+ *   R stub      U_NZentries(Ncores, n, locs, revNNarray, revCondOnLatent, nuggets,
+ *               nuggets_obsord, covType, covparms)             R/RcppExports.R:22-24
+ *   C++ glue    _GPvecchia_U_NZentries(9 SEXP)                 src/RcppExports.cpp:49-67
+ *   C++ kernel  U_NZentries(...)                               src/U_NZentries.cpp:25-118
+ *   consumers   createU()                                      R/createU.R:141-163
+ *               vecchia_likelihood_U() numerator               R/vecchia_likelihood.R:71-76
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch/R types; every function returns a gpv_status;
+ *     gpv_last_error() gives the message of the last failure on the calling thread.
+ *   - all host matrices are COLUMN-MAJOR (R layout): locs[k + N*c], revNN[k + N*j].
+ *   - revNNarray: int32, 1-based location ids, 0 = missing (createU.R:146-147); missing
+ *     entries are compacted exactly as `inds.elem(find(inds))` does (U_NZentries.cpp:44).
+ *   - revCondOnLatent: either R's logical storage (int32: 1 TRUE, 0 FALSE, INT_MIN NA) or the
+ *     coerced double the reference kernel sees (1.0 / 0.0 / NaN): selected by gpv_cond_type.
+ *   - the caller owns every host buffer before and after each call; the library never keeps a
+ *     host pointer past return.  Device memory, streams and events belong to the handle.
+ *   - one thread at a time per handle.  Calls block until outputs are in host memory
+ *     (the *_dev variants are asynchronous on the handle's stream unless stated).
+ *   - a non positive-definite block is NOT an error (U_NZentries.cpp:60-66): its row is left
+ *     zero and counted in *nfail; *first_fail is the smallest failing 0-based row or -1.
+ */
+#ifndef GPVECCHIA_B200_H
+#define GPVECCHIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpv_handle gpv_handle;
+
+typedef enum {
+  GPV_OK = 0,
+  GPV_ERR_ARG = 1,         /* bad argument (null pointer, size, p > GPV_MAX_P, ...) */
+  GPV_ERR_CUDA = 2,        /* CUDA runtime failure; message has the CUDA error string */
+  GPV_ERR_COVTYPE = 3,     /* covType not "matern"/"esqe" (the reference only prints, :27-29) */
+  GPV_ERR_NOMEM = 4,
+  GPV_ERR_UNSUPPORTED = 5  /* valid input outside what this build instantiates */
+} gpv_status;
+
+typedef enum { GPV_COND_RLOGICAL_I32 = 0, GPV_COND_F64 = 1 } gpv_cond_type;
+
+/* covType strings of the reference: "matern" -> covparms (sig2, range, nu), "esqe" ->
+ * (sig2_1, r1, sig2_2, r2).  Matern picks the closed form by exact == on nu (Matern.cpp:32,43,58)
+ * and otherwise the general K_nu branch (:72-83, no sqrt(2 nu) scaling). */
+#define GPV_MAX_P 64
+#define GPV_MAX_D 8
+
+const char* gpv_last_error(void);
+const char* gpv_version(void);
+int gpv_device_count(void);
+
+/* ---- handle: uploads the parameter-free arrays of one vecchia.approx once ------------------
+ * Nlocs, p=m+1, d : shapes of locsord (Nlocs x d) and revNNarray/revCond (Nlocs x p).
+ * obs            : Nlocs R-logical int32 (vecchia.approx$obs, in locsord order), may be NULL
+ *                  when the likelihood numerator is not needed.
+ * row_begin/end  : this handle computes rows [row_begin,row_end) only (multi-GPU sharding by
+ *                  contiguous row range; pass 0,Nlocs for everything).  locs and obs are always
+ *                  uploaded whole (neighbour ids of late rows span the full index range).
+ * device         : CUDA device ordinal. */
+gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                      const int32_t* revNNarray, const void* revCondOnLatent,
+                      gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
+                      int64_t row_end, int device);
+void gpv_destroy(gpv_handle* h);
+
+/* Re-upload revCond (createU.R:83-86 rewrites it per call when some nuggets are zero). */
+gpv_status gpv_set_revcond(gpv_handle* h, const void* revCondOnLatent, gpv_cond_type cond_type);
+
+/* ---- U_NZentries through a handle (host buffers) --------------------------------------------
+ * nuggets[Nlocs] (nuggets.all.ord), nuggets_obsord[n].  Lentries: column-major (row_end-
+ * row_begin) x p, zero-filled beyond n0 like the reference; Zentries[2n] or NULL. */
+gpv_status gpv_u_nzentries(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
+                           const double* nuggets, const double* nuggets_obsord, int64_t n,
+                           double* Lentries, double* Zentries, int64_t* nfail, int64_t* first_fail);
+
+/* Same values, delivered directly in the order createU.R:158-160 builds: for each row of the
+ * shard its n0 values (farthest neighbour first, self last), rows concatenated; if Zentries_tail
+ * != 0 the 2n Z values follow.  out must hold gpv_packed_len(h) (+2n) doubles. */
+int64_t gpv_packed_len(const gpv_handle* h);
+gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, const double* covparms,
+                               int ncovparms, const double* nuggets, const double* nuggets_obsord,
+                               int64_t n, int zentries_tail, double* out, int64_t* nfail,
+                               int64_t* first_fail);
+
+/* ---- fused U + likelihood numerator (vecchia_likelihood.R:74-76), no U materialisation -------
+ * zord[n] = z[ord.z].  skip_rows: the first skip_rows locations are `zy` dummies whose latent
+ * column createU.R:166-171 drops (0 otherwise).  out[0] = quadform.num contribution,
+ * out[1] = logdet.num contribution, out[2] = number of failed rows, all restricted to this
+ * handle's row shard; the obs terms (sum z_i^2/tau_i, sum log tau_i) are added by the handle
+ * whose shard starts at row 0 (include_obs_terms != 0 forces/disables: -1 auto, 0 no, 1 yes). */
+gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, const double* covparms,
+                                int ncovparms, const double* nuggets, const double* nuggets_obsord,
+                                const double* zord, int64_t n, int64_t skip_rows,
+                                int include_obs_terms, double out[3]);
+
+/* ---- device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`) ------
+ * d_nuggets[Nlocs] device pointer.  d_out: row-major (rows x p) when packed == 0, packed order
+ * otherwise.  stream: a cudaStream_t cast to void* (NULL = the handle's own stream).
+ * d_loglik (may be NULL): 3 doubles {quadform rows part, logdet rows part, nfail}; requires
+ * d_zord (n doubles, device) and obs at create time.  d_out may be NULL when only the
+ * likelihood is wanted. */
+gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
+                     const double* d_nuggets, double* d_out, int packed, const double* d_zord,
+                     int64_t skip_rows, double* d_loglik, void* stream);
+
+/* Milliseconds of the last U kernel launch of this handle, from CUDA events recorded on the
+ * launching stream around that launch (synchronises on the stop event). */
+gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms);
+/* Name of the kernel instantiation the last launch used, e.g. "u_sets<P=32,D=2>". */
+const char* gpv_last_kernel_name(const gpv_handle* h);
+/* Number of kernels this library launched since load (monotone counter; bench's gpu_launches). */
+int64_t gpv_launch_count(void);
+
+/* ---- stateless drop-in: the reference's nine arguments, everything uploaded per call ---------
+ * Mirrors U_NZentries(Ncores, n, locs, revNNarray, revCondOnLatent, nuggets, nuggets_obsord,
+ * covType, covparms) (src/U_NZentries.cpp:25); Ncores is accepted and ignored. */
+gpv_status gpv_U_NZentries(int Ncores, int64_t n, int64_t Nlocs, int p, int d, const double* locs,
+                           const int32_t* revNNarray, const void* revCondOnLatent,
+                           gpv_cond_type cond_type, const double* nuggets,
+                           const double* nuggets_obsord, const char* covType,
+                           const double* covparms, int ncovparms, double* Lentries,
+                           double* Zentries, int64_t* nfail, int64_t* first_fail, int device);
+
+/* ---- covariance functions alone (MaternFun / EsqeFun, exported by the reference:
+ * R/RcppExports.R:4-17, src/Matern.cpp:24, src/Esqe.cpp:17).  dist/out: len doubles on host. */
+gpv_status gpv_MaternFun(const double* dist, int64_t len, const double* covparms, double* out,
+                         int device);
+gpv_status gpv_EsqeFun(const double* dist, int64_t len, const double* covparms, double* out,
+                       int device);
+
+/* ---- measurement helpers ---------------------------------------------------------------------
+ * fp64 FMA-pipe peak of `device` from a register-resident DFMA loop (TFLOP/s, 2 flop per FMA)
+ * and a device-to-device copy bandwidth (GB/s, read+write bytes), both timed with CUDA events. */
+gpv_status gpv_measure_fp64_peak(int device, double* tflops);
+gpv_status gpv_measure_copy_bw(int device, double* gbs);
+
+/* ---- harness: synthetic inputs at scale (not part of the reference path) -------
+ * Ordered m-nearest-neighbour search on the GPU: row i gets (i, its min(m,i) nearest among rows
+ * < i, nearest first) -- semantics of GpGp::find_ordered_nn as used at vecchia_specify.R:159 --
+ * written as a column-reversed, 1-based, 0-padded revNNarray (U_sparsity.R:32), column-major,
+ * for rows [row_begin,row_end).  locs column-major Nlocs x d (d = 2 or 3), host. */
+gpv_status gpv_harness_ordered_nn(int64_t Nlocs, int d, int m, const double* locs, int64_t row_begin,
+                                  int64_t row_end, int32_t* revNNarray_out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPVECCHIA_B200_H */

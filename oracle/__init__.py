@@ -11,13 +11,13 @@ by the identities the reference states (exact log-density for m = n-1).  Cholesk
 NN-path U values are **parity unpinned** by the reference's own tests.
 """
 from .ref_c import (MaternFun, EsqeFun, U_NZentries, block_cond_proxy, lib, max_threads,
-                    has_lapack)
+                    has_lapack, RowsProblem)
 from .vecchia_np import (U_sparsity, createU, vecchia_likelihood, vecchia_likelihood_U, U2V,
                          vecchia_specify, whichCondOnLatent, find_ordered_nn_brute,
                          loglik_numerator_from_U, exact_loglik)
 
 __all__ = [
-    "MaternFun", "EsqeFun", "U_NZentries", "block_cond_proxy", "lib", "max_threads", "has_lapack",
+    "MaternFun", "EsqeFun", "U_NZentries", "block_cond_proxy", "lib", "max_threads", "has_lapack", "RowsProblem",
     "U_sparsity", "createU", "vecchia_likelihood", "vecchia_likelihood_U", "U2V",
     "vecchia_specify", "whichCondOnLatent", "find_ordered_nn_brute",
     "loglik_numerator_from_U", "exact_loglik",

@@ -47,6 +47,10 @@ def lib():
                                          dp, ip, dp, dp, dp, C.c_char_p, dp, dp, dp, C.c_int,
                                          C.POINTER(C.c_long)]
     L.gpv_oracle_U_NZentries.restype = C.c_int
+    L.gpv_oracle_U_NZentries_rows.argtypes = [C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, C.c_long,
+                                              C.c_long, dp, ip, dp, dp, dp, C.c_char_p, dp, dp, dp,
+                                              C.c_int, C.POINTER(C.c_long)]
+    L.gpv_oracle_U_NZentries_rows.restype = C.c_int
     L.gpv_oracle_block_cond_proxy.argtypes = [C.c_long, C.c_long, C.c_int, C.c_int, dp, ip, dp, dp,
                                               C.c_char_p, dp]
     L.gpv_oracle_block_cond_proxy.restype = C.c_double
@@ -115,6 +119,43 @@ def U_NZentries(Ncores, n, locs, revNNarray, revCondOnLatent, nuggets, nuggets_o
     if st != 0:
         raise ValueError(f"{covType} covariance is not implemented")
     return dict(Lentries=L.reshape(p, N).T.copy(), Zentries=Z, nfail=int(nfail.value))
+
+
+class RowsProblem:
+    """Pre-marshalled inputs for timing the restated reference on a row range (bench.py's CPU
+    baseline): all array conversion happens here, `run()` is only the C call."""
+
+    def __init__(self, locs, revNN_rows, revCond_rows, row_begin, nuggets, covType, covparms):
+        locs = np.asarray(locs, dtype=np.float64)
+        self.N, self.d = locs.shape
+        self.nrows, self.p = np.asarray(revNN_rows).shape
+        self.row_begin = int(row_begin)
+        self.locs = _colmajor(locs, np.float64)
+        self.nn = _colmajor(revNN_rows, np.int32)
+        rc = np.asarray(revCond_rows)
+        if rc.dtype.kind != "f":
+            rcf = rc.astype(np.float64)
+            rcf[rc < 0] = np.nan
+            rc = rcf
+        self.rc = _colmajor(rc, np.float64)
+        self.nug = _f64(nuggets)
+        self.covType = covType.encode()
+        self.cov = _f64(covparms)
+        self.L = np.zeros(self.nrows * self.p, dtype=np.float64)
+        self.Z = np.zeros(0, dtype=np.float64)
+
+    def run(self, threads, mode=0):
+        nfail = C.c_long(0)
+        st = lib().gpv_oracle_U_NZentries_rows(int(threads), 0, self.N, self.d, self.p, self.row_begin,
+                                               self.nrows, self.locs, self.nn, self.rc, self.nug, self.Z,
+                                               self.covType, self.cov, self.L, self.Z, int(mode),
+                                               C.byref(nfail))
+        if st != 0:
+            raise ValueError("covariance is not implemented")
+        return int(nfail.value)
+
+    def Lentries(self):
+        return self.L.reshape(self.p, self.nrows).T
 
 
 def block_cond_proxy(k, locs, revNNarray, revCondOnLatent, nuggets, covType, covparms):

@@ -250,11 +250,31 @@ void gpv_oracle_EsqeFun_flat(const double* distv, long len, const double* covpar
 //   nfail             out, number of rows whose Cholesky failed (left zero, :64-66)
 // Returns 0, or 1 for an unknown covType (the reference only prints a message, :27-29, and then
 // crashes on an empty covmat; the restatement returns early instead).
+// Row-range form used by bench.py's CPU baseline: revNNarray / revCondOnLatent / Lentries hold only
+// rows [row_begin, row_begin + nrows) (column-major, leading dimension nrows); locs and nuggets are
+// whole.  gpv_oracle_U_NZentries below is the full-range call with the reference's arguments.
+int gpv_oracle_U_NZentries_rows(int Ncores, long n, long Nlocs, int d, int p, long row_begin, long nrows,
+                                const double* locs, const int* revNNarray, const double* revCondOnLatent,
+                                const double* nuggets, const double* nuggets_obsord,
+                                const char* covType, const double* covparms,
+                                double* Lentries, double* Zentries, int mode, long* nfail);
+
 int gpv_oracle_U_NZentries(int Ncores, long n, long Nlocs, int d, int p,
                            const double* locs, const int* revNNarray, const double* revCondOnLatent,
                            const double* nuggets, const double* nuggets_obsord,
                            const char* covType, const double* covparms,
                            double* Lentries, double* Zentries, int mode, long* nfail) {
+  return gpv_oracle_U_NZentries_rows(Ncores, n, Nlocs, d, p, 0, Nlocs, locs, revNNarray, revCondOnLatent,
+                                     nuggets, nuggets_obsord, covType, covparms, Lentries, Zentries, mode,
+                                     nfail);
+}
+
+int gpv_oracle_U_NZentries_rows(int Ncores, long n, long Nlocs, int d, int p, long row_begin, long nrows,
+                                const double* locs, const int* revNNarray, const double* revCondOnLatent,
+                                const double* nuggets, const double* nuggets_obsord,
+                                const char* covType, const double* covparms,
+                                double* Lentries, double* Zentries, int mode, long* nfail) {
+  (void)row_begin;  // ids inside revNNarray are global; the range only selects which rows are present
   CovKind kind = COV_UNKNOWN;
   if (std::strcmp(covType, "matern") == 0) kind = COV_MATERN;
   else if (std::strcmp(covType, "esqe") == 0) kind = COV_ESQE;
@@ -263,23 +283,23 @@ int gpv_oracle_U_NZentries(int Ncores, long n, long Nlocs, int d, int p,
     return 1;
   }
   const int m = p - 1;                                       // :31
-  std::memset(Lentries, 0, sizeof(double) * (size_t)Nlocs * p);  // :33
+  std::memset(Lentries, 0, sizeof(double) * (size_t)nrows * p);  // :33
   long fails = 0;
   const bool use_lapack = (mode == 0) && g_dpotrf && g_dtrtrs;
   if (Ncores < 1) Ncores = 1;
 
 #pragma omp parallel for num_threads(Ncores) schedule(static) reduction(+ : fails)
-  for (long k = 0; k < Nlocs; ++k) {                         // :39
+  for (long k = 0; k < nrows; ++k) {                         // :39
     std::vector<long> inds00; inds00.reserve(p);
     for (int j = 0; j < p; ++j) {                            // :41-44  find(inds) - 1
-      int id = revNNarray[k + (size_t)j * Nlocs];
+      int id = revNNarray[k + (size_t)j * nrows];
       if (id != 0) inds00.push_back((long)id - 1);
     }
     const int n0 = (int)inds00.size();                       // :45
     if (n0 == 0) continue;
     std::vector<double> nug(n0);                             // :47
     for (int j = 0; j < n0; ++j) {
-      double rc = revCondOnLatent[k + (size_t)(m + 1 - n0 + j) * Nlocs];
+      double rc = revCondOnLatent[k + (size_t)(m + 1 - n0 + j) * nrows];
       nug[j] = nuggets[inds00[j]] * (1.0 - rc);
     }
     if (mode != 2) {
@@ -305,7 +325,7 @@ int gpv_oracle_U_NZentries(int Ncores, long n, long Nlocs, int d, int p,
         if (info == 0) trsv_upper<double>(covmat.data(), n0, onevec.data());
       }
       if (info == 0) {                                       // :63
-        for (int j = 0; j < n0; ++j) Lentries[k + (size_t)j * Nlocs] = onevec[j];
+        for (int j = 0; j < n0; ++j) Lentries[k + (size_t)j * nrows] = onevec[j];
       } else {
         fails += 1;                                          // :64-66 row stays zero
       }
@@ -323,7 +343,7 @@ int gpv_oracle_U_NZentries(int Ncores, long n, long Nlocs, int d, int p,
       int info = potf2_upper<Q>(covmat.data(), n0, [](Q v) { return sqrtq(v); });
       if (info == 0) {
         trsv_upper<Q>(covmat.data(), n0, onevec.data());
-        for (int j = 0; j < n0; ++j) Lentries[k + (size_t)j * Nlocs] = (double)onevec[j];
+        for (int j = 0; j < n0; ++j) Lentries[k + (size_t)j * nrows] = (double)onevec[j];
       } else {
         fails += 1;
       }

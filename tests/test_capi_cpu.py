@@ -1,0 +1,94 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/*.h declares,
+reports errors through status codes (no compute calls need a GPU here), and its general-nu
+machinery (host-compiled copy of the same routines) matches mpmath."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gpvecchia_b200 as G
+from gpvecchia_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gpvecchia_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpv_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for nm in names:
+        assert hasattr(G.lib, nm), f"{nm} declared in include/gpvecchia_b200.h but not exported"
+    assert sorted(_lib.EXPORTED) == names
+
+
+def test_version_and_counters():
+    assert b"sm_100a" in G.lib.gpv_version()
+    assert G.lib.gpv_launch_count() >= 0
+    assert G.lib.gpv_device_count() >= 0
+
+
+def test_bad_arguments_are_status_codes_not_crashes():
+    h = C.c_void_p()
+    st = G.lib.gpv_create(C.byref(h), 10, 3, 2, None, None, None, 0, None, 0, 10, 0)
+    assert st == _lib.GPV_ERR_ARG and b"null" in G.lib.gpv_last_error()
+    x = np.zeros(20)
+    nn = np.zeros(30, dtype=np.int32)
+    st = G.lib.gpv_create(C.byref(h), 10, 65, 2, x.ctypes.data, nn.ctypes.data, nn.ctypes.data, 0, None, 0, 10, 0)
+    assert st == _lib.GPV_ERR_ARG and b"GPV_MAX_P" in G.lib.gpv_last_error()
+    st = G.lib.gpv_create(C.byref(h), 10, 3, 2, x.ctypes.data, nn.ctypes.data, nn.ctypes.data, 0, None, 5, 3, 0)
+    assert st == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_packed_len(None) == 0
+    G.lib.gpv_destroy(None)
+
+
+def test_unknown_covtype_is_an_error_before_touching_the_device():
+    # the reference only prints (U_NZentries.cpp:27-29); the boundary returns GPV_ERR_COVTYPE
+    with pytest.raises(G.GpvError) as ei:
+        G.U_NZentries(1, 1, np.zeros((1, 2)), np.array([[1]]), np.array([[1]]), [0.1], [0.1], "gauss", [1, 1, 1])
+    assert ei.value.status == _lib.GPV_ERR_COVTYPE
+    assert "gauss covariance is not implemented" in str(ei.value)
+
+
+@pytest.mark.skipif(G.lib.gpv_device_count() > 0, reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_a_gpu():
+    with pytest.raises(G.GpvError) as ei:
+        G.U_NZentries(1, 1, np.zeros((1, 2)), np.array([[1]]), np.array([[1]]), [0.1], [0.1], "matern", [1, 1, 1.5])
+    assert ei.value.status == _lib.GPV_ERR_CUDA
+
+
+def test_general_nu_evaluator_against_mpmath_golden():
+    rows = json.load(open(os.path.join(GOLD, "matern_general_mpmath.json")))["rows"]
+    worst = 0.0
+    for nu, s, val in rows:
+        got = G.lib.gpv_selftest_matern_general_host(s, 1.0, nu)
+        if val == 0.0:
+            assert abs(got) < 1e-300
+            continue
+        worst = max(worst, abs(got - val) / abs(val) / max(1.0, s))
+    assert worst < 1e-14, worst       # relative error <= 1e-14 * max(1, s), any nu incl. near-integers
+
+
+def test_general_nu_table_against_mpmath_golden():
+    rows = json.load(open(os.path.join(GOLD, "matern_general_mpmath.json")))["rows"]
+    rng_, wmax = 0.004, 2.0
+    worst = 0.0
+    for nu, s, val in rows:
+        w = (s * rng_) ** 2
+        s_eff = np.sqrt(w) / rng_
+        if val == 0.0 or abs(s_eff - s) > 1e-14 * s:
+            pass
+        got = G.lib.gpv_selftest_table_eval_host(w, 1.0, rng_, nu, wmax)
+        if val == 0.0:
+            continue
+        # forming w = (s*range)^2 and back perturbs s by ~2 ulp: allow s*4e-16 on top of 1e-14
+        worst = max(worst, abs(got - val) / abs(val) / max(1.0, s))
+    assert worst < 2e-14, worst

@@ -1,0 +1,315 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): nonzero pattern and indices bit-exact; U values within 1e-10
+relative (row-max-scaled); likelihood terms within 1e-8 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import gpvecchia_b200 as G
+import oracle as O
+from gpvecchia_b200 import harness as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+VAL_TOL = 1e-10
+LL_TOL = 1e-8
+
+
+def _rc_double(revCond):
+    rc = revCond.astype(np.float64)
+    rc[revCond < 0] = np.nan
+    return rc
+
+
+def _rowscaled_err(got, ref):
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    return float((np.abs(got - ref) / scale).max())
+
+
+def _problem(n, m, d, cond_yz, stream):
+    locs = H.make_locs(n, d, stream=stream)
+    if cond_yz == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        return H.make_vecchia_approx(locs2, NN, Cond, obs, "zy")
+    NN = H.ordered_nn_kdtree(locs, m)
+    if cond_yz == "SGV":
+        Cond = O.whichCondOnLatent(NN)
+    else:
+        Cond = H.layout_yz(NN, cond_yz)
+    return H.make_vecchia_approx(locs, NN, Cond, np.ones(n, dtype=bool), cond_yz)
+
+
+def _both(va, covType, covparms, nug_all, nug_obs):
+    prep = va["U_prep"]
+    n = int(va["obs"].sum())
+    got = G.U_NZentries(1, n, va["locsord"], prep["revNNarray"], prep["revCond"], nug_all, nug_obs,
+                        covType, covparms)
+    ref = O.U_NZentries(O.max_threads(), n, va["locsord"], prep["revNNarray"], _rc_double(prep["revCond"]),
+                        nug_all, nug_obs, covType, np.asarray(covparms, float))
+    return got, ref
+
+
+COVS = [("matern", [1.0, None, 0.5]), ("matern", [1.3, None, 1.5]), ("matern", [0.8, None, 2.5]),
+        ("matern", [1.0, None, 0.8]), ("matern", [1.0, None, 1.3]), ("matern", [1.1, None, 3.2]),
+        ("esqe", [0.7, None, 0.4, None])]
+
+
+def _fill_range(cp, rng_):
+    return [rng_ if v is None else v for v in cp]
+
+
+@pytest.mark.parametrize("covType,cp", COVS)
+def test_cfg2_shape_all_covariances(covType, cp):
+    n, m, d = 4000, 30, 2
+    va = _problem(n, m, d, "z", stream=2)
+    cp = _fill_range(cp, H.default_range(n, d))
+    nug = H.make_nuggets(n, stream=2)
+    got, ref = _both(va, covType, cp, nug, nug)
+    assert ref["nfail"] == 0 and got["nfail"] == 0
+    assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+    assert np.array_equal(got["Zentries"], ref["Zentries"]) or np.allclose(got["Zentries"], ref["Zentries"], rtol=2e-16, atol=0)
+
+
+def test_cfg1_zy_layout_createU_and_likelihood():
+    # BASELINE configs[0] at reduced n: vecchia_specify + vecchia_likelihood, 2-D, m=20, nu=1.5, zy
+    n, m = 2000, 20
+    va = _problem(n, m, 2, "zy", stream=1)
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    z = H.make_data(n, stream=1)
+    tau = H.make_nuggets(n, stream=1)
+    Ug = G.createU(va, cp, tau)
+    Uo = O.createU(va, cp, tau)
+    A, B = Ug["U"].tocsc(), Uo["U"].tocsc()
+    A.sort_indices(); B.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)   # pattern bit-exact
+    assert np.array_equal(Ug["latent"], Uo["latent"]) and np.array_equal(Ug["obs"], Uo["obs"])
+    colmax = np.maximum.reduceat(np.abs(B.data), B.indptr[:-1])
+    scale = np.repeat(colmax, np.diff(B.indptr))
+    assert (np.abs(A.data - B.data) / scale).max() < VAL_TOL
+    q, l, nf = G.vecchia_loglik_numerator(z, va, cp, tau)
+    qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
+    assert nf == 0 and abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
+    with pytest.warns(UserWarning):
+        ll = G.vecchia_likelihood(z, va, cp, tau)
+    llr = O.vecchia_likelihood_U(z, Uo)
+    assert abs(ll - llr) <= LL_TOL * abs(llr)
+
+
+@pytest.mark.parametrize("cond_yz", ["y", "z", "SGV"])
+def test_full_loglik_against_oracle_and_exact(cond_yz):
+    n, m = 600, 15
+    va = _problem(n, m, 2, cond_yz, stream=6)
+    cp = [1.2, 0.15, 1.5]
+    z = H.make_data(n, stream=6)
+    ll = G.vecchia_likelihood(z, va, cp, 0.1)
+    llr = O.vecchia_likelihood(z, va, cp, 0.1)
+    assert abs(ll - llr) <= LL_TOL * abs(llr)
+    q, l, _ = G.vecchia_loglik_numerator(z, va, cp, 0.1)
+    qr, lr, _ = O.loglik_numerator_from_U(z, O.createU(va, cp, 0.1))
+    assert abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
+
+
+def test_known_answer_full_conditioning_exact_density():
+    # m = n-1 => exact Gaussian log-density (vignette :128-139); n-1 = 30 keeps p = 31
+    n = 31
+    locs = H.make_locs(n, 2, stream=7)
+    z = H.make_data(n, stream=7)
+    for cyz in ("y", "z", "SGV"):
+        NN = H.ordered_nn_kdtree(locs, n - 1)
+        Cond = O.whichCondOnLatent(NN) if cyz == "SGV" else H.layout_yz(NN, cyz)
+        va = H.make_vecchia_approx(locs, NN, Cond, np.ones(n, dtype=bool), cyz)
+        for cp in ([1.3, 0.25, 1.5], [1.3, 0.25, 0.8], [1.0, 0.3, 2.5]):
+            ll = G.vecchia_likelihood(z, va, cp, 0.2)
+            ex = O.exact_loglik(z, locs, cp, 0.2)
+            assert abs(ll - ex) <= LL_TOL * abs(ex), (cyz, cp)
+
+
+def test_quad_precision_fixture():
+    f = np.load(os.path.join(GOLD, "u_small_quad.npz"))
+    n = f["locs"].shape[0]
+    for tag, ct in [("m05", "matern"), ("m15", "matern"), ("m25", "matern"), ("g08", "matern"),
+                    ("g13", "matern"), ("esqe", "esqe")]:
+        got = G.U_NZentries(1, n, f["locs"], f["revNNarray"], f["revCond"], f["nuggets"], f["nuggets"],
+                            ct, f["cp_" + tag])
+        gold = f["L_" + tag]
+        assert np.array_equal(got["Lentries"] == 0, gold == 0), tag
+        assert _rowscaled_err(got["Lentries"], gold) < VAL_TOL, tag
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 7, 10, 12, 15, 20, 25, 30, 31])
+def test_every_instantiated_set_size(m):
+    n = 1500
+    va = _problem(n, m, 2, "SGV" if m <= 10 else "z", stream=10 + m)
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    nug = np.full(n, 0.1)
+    got, ref = _both(va, "matern", cp, nug, nug)
+    assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5])
+def test_spatial_dimensions(d):
+    n, m = 1200, 10
+    va = _problem(n, m, d, "z", stream=40 + d)
+    cp = [1.0, H.default_range(n, d), 2.5]
+    nug = np.full(n, 0.05)
+    got, ref = _both(va, "matern", cp, nug, nug)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+    cp = [0.6, H.default_range(n, d), 0.5, 0.7 * H.default_range(n, d)]
+    got, ref = _both(va, "esqe", cp, nug, nug)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+
+
+def test_edge_duplicates_zero_inf_and_negative_nuggets():
+    n, m = 400, 8
+    locs = H.make_locs(n, 2, stream=50)
+    locs[100:110] = locs[90:100]              # exact duplicates: D == 0 off the diagonal
+    NN = H.ordered_nn_kdtree(locs, m)
+    va = H.make_vecchia_approx(locs, NN, H.layout_yz(NN, "z"), np.ones(n, dtype=bool), "z")
+    cp = [1.0, 0.2, 1.5]
+    nug = np.full(n, 0.1)
+    nug[5] = 0.0                               # zero nugget (createU.R:83-86 territory)
+    nug[7] = np.inf                            # VL missing data (vecchia_laplace_NR.R:108)
+    nug[300] = -40.0                           # indefinite blocks -> zero rows (U_NZentries.cpp:64-66)
+    got, ref = _both(va, "matern", cp, nug, np.abs(nug))
+    assert got["nfail"] == ref["nfail"] > 0
+    bad = np.nonzero(np.all(ref["Lentries"] == 0, axis=1))[0]
+    assert got["first_fail"] == bad.min()
+    assert np.all(got["Lentries"][bad] == 0)
+    ok = np.ones(n, dtype=bool); ok[bad] = False
+    assert np.array_equal(np.isnan(got["Lentries"]), np.isnan(ref["Lentries"]))
+    fin = np.isfinite(ref["Lentries"]).all(axis=1) & ok
+    assert _rowscaled_err(got["Lentries"][fin], ref["Lentries"][fin]) < VAL_TOL
+    # Z entries: 0 nugget -> -/+Inf, Inf nugget -> -/+0 (U_NZentries.cpp:112-113)
+    assert np.array_equal(got["Zentries"], ref["Zentries"])
+
+
+def test_zero_nugget_createU_trimming():
+    n, m = 300, 6
+    va = _problem(n, m, 2, "SGV", stream=51)
+    tau = np.full(n, 0.1)
+    tau[[3, 50, 299]] = 0.0
+    cp = [1.0, 0.2, 1.5]
+    Ug, Uo = G.createU(va, cp, tau), O.createU(va, cp, tau)
+    A, B = Ug["U"].tocsc(), Uo["U"].tocsc()
+    A.sort_indices(); B.sort_indices()
+    assert A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    assert np.allclose(A.data, B.data, rtol=1e-9, atol=0)
+    for k in ("inds_U", "inds_z", "inds_locs"):
+        assert np.array_equal(Ug["zero_nugg"][k], Uo["zero_nugg"][k])
+    assert np.array_equal(Ug["latent"], Uo["latent"]) and np.array_equal(Ug["ord"], Uo["ord"])
+
+
+def test_missing_entries_anywhere_are_compacted_like_find():
+    # `inds.elem(find(inds))` (U_NZentries.cpp:44) compacts zeros wherever they are; revCond is read
+    # from the LAST n0 columns (:47)
+    n, m = 200, 6
+    va = _problem(n, m, 2, "z", stream=52)
+    prep = va["U_prep"]
+    rnn = prep["revNNarray"].copy()
+    rnn[50:120:7, 2] = 0
+    rnn[60:130:9, 0] = 0
+    nug = np.full(n, 0.1)
+    cp = [1.0, 0.3, 0.5]
+    got = G.U_NZentries(1, n, va["locsord"], rnn, prep["revCond"], nug, nug, "matern", cp)
+    ref = O.U_NZentries(1, n, va["locsord"], rnn, _rc_double(prep["revCond"]), nug, nug, "matern", np.array(cp))
+    assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+
+
+def test_handle_reuse_packed_order_and_row_shards():
+    n, m = 3000, 12
+    va = _problem(n, m, 2, "z", stream=53)
+    prep = va["U_prep"]
+    nug = H.make_nuggets(n, stream=53)
+    obs = np.ones(n, dtype=bool)
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=obs) as h:
+        outs = {}
+        for cp in ([1.0, 0.05, 1.5], [2.0, 0.08, 0.5], [1.0, 0.05, 1.7]):
+            r = h.U_NZentries("matern", cp, nug, nug)
+            ref = O.U_NZentries(2, n, va["locsord"], prep["revNNarray"], _rc_double(prep["revCond"]), nug, nug,
+                                "matern", np.array(cp))
+            assert _rowscaled_err(r["Lentries"], ref["Lentries"]) < VAL_TOL
+            packed, nf, _ = h.values_packed("matern", cp, nug, nug)
+            not_na = (prep["revNNarray"][:, ::-1] != 0).ravel()
+            want = np.concatenate([r["Lentries"].ravel()[not_na], r["Zentries"]])   # createU.R:158-160
+            assert np.array_equal(packed, want)
+            outs[tuple(cp)] = r["Lentries"]
+        assert "u_sets" in h.last_kernel_name() and h.last_kernel_ms() > 0
+        full = outs[(1.0, 0.05, 1.5)]
+    cuts = [0, 1, 17, 1000, 1000, 3000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=obs, row_begin=a, row_end=b) as hs:
+            r = hs.U_NZentries("matern", [1.0, 0.05, 1.5], nug, nug)
+            assert r["Lentries"].shape == (b - a, m + 1)
+            assert np.array_equal(r["Lentries"], full[a:b])      # same kernel, same rows: bit-identical
+
+
+def test_sharded_loglik_partials_sum_to_the_whole():
+    n, m = 4000, 10
+    va = _problem(n, m, 2, "z", stream=54)
+    prep = va["U_prep"]
+    nug = H.make_nuggets(n, stream=54)
+    z = H.make_data(n, stream=54)
+    obs = np.ones(n, dtype=bool)
+    cp = [1.0, 0.04, 0.8]
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=obs) as h:
+        q, l, nf = h.loglik_numerator("matern", cp, nug, nug, z)
+    qs = ls = 0.0
+    for a, b in ((0, 1300), (1300, 2600), (2600, 4000)):
+        with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=obs, row_begin=a, row_end=b) as hs:
+            qq, lll, _ = hs.loglik_numerator("matern", cp, nug, nug, z)
+            qs += qq; ls += lll
+    assert abs(qs - q) <= 1e-12 * abs(q) and abs(ls - l) <= 1e-12 * abs(l)
+    Uo = O.createU(va, cp, nug)
+    qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
+    assert abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
+
+
+def test_covariance_functions_alone():
+    # the reference's test-MaternFun.r, against the device functions
+    locs = H.make_locs(100, 2, stream=55)
+    D = np.sqrt(((locs[:, None] - locs[None]) ** 2).sum(-1))
+    for nu in (0.5, 1.5, 2.5):
+        assert np.abs(G.MaternFun(D, [1.0, 0.2, nu]) - O.MaternFun(D, [1.0, 0.2, nu])).sum() < 1e-10
+    for nu in (0.3, 0.8, 1.3, 4.1):
+        a, b = G.MaternFun(D, [1.0, 0.2, nu]), O.MaternFun(D, [1.0, 0.2, nu])
+        assert np.abs(a - b).sum() < 1e-10 and (np.abs(a - b) / b).max() < 1e-12
+    cp = [0.7, 0.2, 0.4, 0.1]
+    assert np.abs(G.EsqeFun(D, cp) - O.EsqeFun(D, cp)).sum() < 1e-10
+    assert G.MaternFun(np.zeros(4), [2.5, 0.2, 0.8]).tolist() == [2.5] * 4
+
+
+def test_scale_property_at_larger_n():
+    # size-independent property: cov -> c*cov (sig2 and nuggets scaled by c) => U -> U / sqrt(c)
+    n, m = 60000, 30
+    locs = H.make_locs(n, 2, stream=56)
+    NN = H.ordered_nn_kdtree(locs, m)
+    revNN = H.rev(NN)
+    revCond = H.rev(H.layout_yz(NN, "z"))
+    nug = H.make_nuggets(n, stream=56)
+    c = 4.0
+    with G.UHandle(locs, revNN, revCond) as h:
+        rng_ = H.default_range(n, 2)
+        a = h.U_NZentries("matern", [1.0, rng_, 1.5], nug, nug)["Lentries"]
+        b = h.U_NZentries("matern", [c, rng_, 1.5], c * nug, c * nug)["Lentries"]
+    assert _rowscaled_err(b * np.sqrt(c), a) < 1e-12
+    # diagonal of U is positive, rows beyond n0 are zero
+    assert np.all(a[:, -1][m:] > 0)
+
+
+@pytest.mark.parametrize("d,m,n", [(2, 30, 50000), (3, 12, 20000), (1, 5, 5000), (2, 3, 1000)])
+def test_harness_gpu_ordered_nn_matches_host_search(d, m, n):
+    # harness, not the reference path: the GPU grid search must produce the arrays the host
+    # (cKDTree / brute force) search produces, bit for bit, including a row shard
+    locs = H.make_locs(n, d, stream=60 + d)
+    ref = H.rev(H.ordered_nn_kdtree(locs, m))
+    got = H.ordered_nn_gpu(locs, m)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    a, b = n // 3, n // 3 + 777
+    assert np.array_equal(H.ordered_nn_gpu(locs, m, a, b), ref[a:b])
