@@ -51,13 +51,13 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
@@ -66,10 +66,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm, mx, reasons = [], 0.0, set()
         for r in self.rows:
@@ -221,7 +221,12 @@ def main():
     d_out = torch.empty(nrows * p, dtype=torch.float64, device=dev)
     d_z = torch.from_numpy(z).to(dev)
     d_ll = torch.zeros(3, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: its handle is what the C ABI launches on, and the
+    # torch events below are recorded on the same stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_dev():
         h.u_dev("matern", covparms, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)

@@ -88,9 +88,17 @@ def test_cfg1_zy_layout_createU_and_likelihood():
     A.sort_indices(); B.sort_indices()
     assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)   # pattern bit-exact
     assert np.array_equal(Ug["latent"], Uo["latent"]) and np.array_equal(Ug["obs"], Uo["obs"])
-    colmax = np.maximum.reduceat(np.abs(B.data), B.indptr[:-1])
-    scale = np.repeat(colmax, np.diff(B.indptr))
-    assert (np.abs(A.data - B.data) / scale).max() < VAL_TOL
+    # zy rows condition on latent y (no nugget) and hold a duplicated location (y_i, z_i): blocks are
+    # ill conditioned, so two correct fp64 implementations differ by cond*eps.  Arbitrate with the
+    # __float128 oracle: the CUDA path must be as close to it as the fp64 restatement.
+    Uq = O.createU(va, cp, tau, mode=2)["U"].tocsc()
+    Uq.sort_indices()
+    colmax = np.maximum.reduceat(np.abs(Uq.data), Uq.indptr[:-1])
+    scale = np.repeat(colmax, np.diff(Uq.indptr))
+    err_gpu = (np.abs(A.data - Uq.data) / scale).max()
+    err_ref = (np.abs(B.data - Uq.data) / scale).max()
+    assert err_gpu < max(VAL_TOL, 3 * err_ref), (err_gpu, err_ref)
+    assert (np.abs(A.data - B.data) / scale).max() < 1e-8
     q, l, nf = G.vecchia_loglik_numerator(z, va, cp, tau)
     qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
     assert nf == 0 and abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
@@ -176,7 +184,14 @@ def test_edge_duplicates_zero_inf_and_negative_nuggets():
     nug[5] = 0.0                               # zero nugget (createU.R:83-86 territory)
     nug[7] = np.inf                            # VL missing data (vecchia_laplace_NR.R:108)
     nug[300] = -40.0                           # indefinite blocks -> zero rows (U_NZentries.cpp:64-66)
-    got, ref = _both(va, "matern", cp, nug, np.abs(nug))
+    got, _ = _both(va, "matern", cp, nug, np.abs(nug))
+    # Row 8 has an Inf self-nugget times (1 - revCond) = 0 -> NaN diagonal (U_NZentries.cpp:47).
+    # Reference LAPACK's dpotrf/dpotf2 tests `ajj <= 0 || disnan(ajj)` and fails, chol() throws and
+    # the row stays zero; the OpenBLAS build inside scipy skips the NaN test and returns a NaN row.
+    # The CUDA path follows published LAPACK, i.e. oracle mode 1 (textbook dpotf2).
+    prep = va["U_prep"]
+    ref = O.U_NZentries(2, n, va["locsord"], prep["revNNarray"], _rc_double(prep["revCond"]), nug, np.abs(nug),
+                        "matern", np.array(cp), mode=1)
     assert got["nfail"] == ref["nfail"] > 0
     bad = np.nonzero(np.all(ref["Lentries"] == 0, axis=1))[0]
     assert got["first_fail"] == bad.min()
@@ -311,5 +326,5 @@ def test_harness_gpu_ordered_nn_matches_host_search(d, m, n):
     ref = H.rev(H.ordered_nn_kdtree(locs, m))
     got = H.ordered_nn_gpu(locs, m)
     assert got.shape == ref.shape and np.array_equal(got, ref)
-    a, b = n // 3, n // 3 + 777
+    a, b = n // 3, min(n, n // 3 + 777)
     assert np.array_equal(H.ordered_nn_gpu(locs, m, a, b), ref[a:b])
