@@ -229,7 +229,7 @@ __device__ __forceinline__ double cov_general(double r2, const UParams& q) {
   double acc = __ldg(cf + (size_t)kTabDeg * t.nint);
 #pragma unroll
   for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + (size_t)k * t.nint));
-  if (r2 >= t.w_split) acc *= exp(-sqrt(r2) * q.inv_range);
+  if (r2 >= t.w_split) acc *= exp_neg(sqrt_nonneg(r2) * q.inv_range);
   return acc;
 }
 

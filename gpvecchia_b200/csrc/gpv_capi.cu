@@ -71,6 +71,9 @@ static void register_all() {
   register_kernels_P26(g_entries, &g_nentries);
   register_kernels_P31(g_entries, &g_nentries);
   register_kernels_P32(g_entries, &g_nentries);
+  register_kernels_P41(g_entries, &g_nentries);
+  register_kernels_P51(g_entries, &g_nentries);
+  register_kernels_P64(g_entries, &g_nentries);
 }
 const KernelEntry* select_kernel(int p, int d) {
   std::call_once(g_reg_once, register_all);
@@ -384,7 +387,7 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   H_TRY(cudaFuncSetAttribute((const void*)entry->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              entry->smem_bytes));
   H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, (const void*)entry->kernel,
-                                                      kWarpsPerBlock * 32, entry->smem_bytes));
+                                                      kThreadsPerBlock, entry->smem_bytes));
   if (h->blocks_per_sm < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry->name); }
   h->max_blocks = h->num_sms * h->blocks_per_sm;
 
@@ -609,7 +612,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
   g_launches++;
   CUDA_TRY(cudaEventRecord(h->ev_start, st));
-  e->kernel<<<blocks, kWarpsPerBlock * 32, e->smem_bytes, st>>>(q);
+  e->kernel<<<blocks, kThreadsPerBlock, e->smem_bytes, st>>>(q);
   g_launches++;
   CUDA_TRY(cudaEventRecord(h->ev_stop, st));
   CUDA_TRY(cudaGetLastError());

@@ -26,5 +26,8 @@ void register_kernels_P21(KernelEntry* out, int* n);
 void register_kernels_P26(KernelEntry* out, int* n);
 void register_kernels_P31(KernelEntry* out, int* n);
 void register_kernels_P32(KernelEntry* out, int* n);
+void register_kernels_P41(KernelEntry* out, int* n);
+void register_kernels_P51(KernelEntry* out, int* n);
+void register_kernels_P64(KernelEntry* out, int* n);
 
 }  // namespace gpv

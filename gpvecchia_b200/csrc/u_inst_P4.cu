@@ -1,3 +1,3 @@
 #define GPV_INST_P 4
-#define GPV_INST_G 8
+#define GPV_INST_G 4
 #include "u_inst.inc"

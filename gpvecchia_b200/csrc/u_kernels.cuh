@@ -5,26 +5,28 @@
 // src/Esqe.cpp:17-39 -> chol(.,"upper") + solve(R, e_last) :60-63) and the numerator of
 // vecchia_likelihood_U (R/vecchia_likelihood.R:74-76).
 //
-// Design: one lane-group of G lanes (G = 8/16/32 -> 4/2/1 sets per warp) per
-// conditioning set; P = padded set size (compile time, P <= G).
-//   1. ids of the row loaded coalesced and compacted like `inds.elem(find(inds))`
-//      (U_NZentries.cpp:44); missing entries become LEADING identity padding, so "self is last"
-//      (index P-1) is preserved;
-//   2. coordinates + nuggets gathered once per neighbour, staged in shared memory;
-//   3. the P(P-1)/2 unique covariances are evaluated balanced over the lanes (lane i handles the
-//      pairs (i, i+t mod P), t = 1..P/2), staged in shared memory, then every lane pulls ITS ROW
-//      of the lower triangle into registers;
-//   4. right-looking Cholesky, row-per-lane in registers; column k of L is published through
-//      shared memory and consumed by warp-broadcast (vectorised) loads: one DFMA per (k, j) per
-//      group, no shuffles in the update loop;
-//   5. x = L^{-T} e_P by a column sweep over the shared-memory copy of L (odd leading dimension,
-//      conflict-free), which is the reference's solve(R, onevec);
-//   6. outputs: U values (row-major zero-filled, or packed createU.R:158-160 order) and/or the
-//      fused likelihood terms, reduced deterministically per block.
-// Bound by the fp64 FMA pipe; tensor cores are not used (batched tiny factorisations).
+// Design (DESIGN.md has the measurements that led here):
+//   * a lane group of G lanes owns one conditioning set; P = padded set size (compile time) and
+//     G >= ceil(P/2): G = 16 for P <= 32 (two sets per warp), 32 for P <= 64, 8 / 4 for small P.
+//   * FOLDED ROWS: lane q keeps two rows of the lower triangle in registers, row q ("low") and row
+//     P-1-q ("high"), so every lane carries ~P+1 entries: the triangular load imbalance of a
+//     row-per-lane Cholesky disappears and a warp instruction serves 32/G sets.
+//   * missing neighbours become LEADING identity padding, so "self is last" (index P-1) holds and
+//     the compaction is exactly `inds.elem(find(inds))` (U_NZentries.cpp:44).
+//   * the P(P-1)/2 unique covariances are evaluated balanced (point i handles (i, i+t mod P),
+//     t = 1..P/2; each lane runs its two points in the same iteration for ILP), staged in shared
+//     memory column-major (even stride: conflict-free stores), then pulled into registers.
+//   * right-looking Cholesky: column k of L is published to shared memory (contiguous) and read
+//     back as group-broadcast 16-byte loads; one DFMA per (k, j) per row kind, no shuffles in the
+//     update loop.  x = L^{-T} e_P is a column sweep over the same shared copy (odd stride:
+//     conflict-free), which is the reference's solve(R, onevec).
+//   * sqrt / exp / rsqrt are branch-free inline sequences (MUFU seed + FMA refinement): the
+//     kernel is issue-slot and fp64-pipe bound, so library slow paths are not affordable.
+// Tensor cores are not used: batched 31x31 fp64 factorisations, not a dense contraction.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "exp_coeffs.h"
 
 #ifndef GPV_MAX_D
 #define GPV_MAX_D 8
@@ -35,17 +37,14 @@ namespace gpv {
 enum CovKind : int { COV_EXP = 0, COV_M15 = 1, COV_M25 = 2, COV_ESQE = 3, COV_GENERAL = 4 };
 
 // Piecewise-polynomial table of the general-nu Matern (built per call, bessel_table.cuh).
-// Variable: w = squared distance.  Interval index from the exponent and the top `sub_bits`
-// mantissa bits of w; local variable v = mantissa(w) - centre in [-2^-(sub_bits+1), +..).
 struct CovTable {
   const double* coef;   // [deg+1][nint], coefficient-major
   int nint;
   int idx0;             // (hi32(w) >> (20 - sub_bits)) - idx0 = interval index
   int sub_bits;
   int deg;
-  double w_split;       // w > w_split : table holds exp(+s) * cov, multiply by exp(-s)
-  // constants for the direct (out-of-table) evaluator, Temme / Steed CF2
-  double nu, xmu, gam1, gam2, gampl, gammi, normcon;
+  double w_split;       // w >= w_split : table holds exp(+s) * cov, multiply by exp(-s)
+  double nu, xmu, gam1, gam2, gampl, gammi, normcon;   // direct (out-of-table) evaluator
   int nl;
 };
 
@@ -68,12 +67,70 @@ struct UParams {
   long long* first_fail;
   int cov;                // CovKind
   double c0;              // covariance at distance 0
-  double c1, c2, c3, c4;  // kind-specific constants (host: make_cov_constants)
+  double c1, c2, c3, c4;  // kind-specific constants (host: setup_cov)
   double inv_range;       // general branch
   CovTable tab;
 };
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kThreadsPerBlock = 128;
+constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
+
+// --------------------------------------------------------------------------------------------
+// branch-free fp64 primitives
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_seed(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, ~20 good bits
+  return y;
+}
+// 1/sqrt(a) for finite normal a > 0 to ~1 ulp: cubic step then a Newton step.
+// a = +Inf returns +0 (seed is +0, refinement is skipped by the select); a <= 0 / NaN: garbage,
+// callers test `a > 0` themselves.
+__device__ __forceinline__ double rsqrt_pos(double a) {
+  const double y0 = rsqrt_seed(a);
+  const double t = a * y0;
+  const double e = fma(-t, y0, 1.0);
+  const double y1 = fma(fma(e, 0.375, 0.5), e * y0, y0);     // error ~ e^3
+  const double t1 = a * y1;
+  const double e1 = fma(-t1, y1, 1.0);
+  const double y2 = fma(0.5 * e1, y1, y1);
+  return (a < 1.7976931348623157e308) ? y2 : 0.0;
+}
+// sqrt(w) for w >= 0 (w == 0 or denormal -> 0) to ~1 ulp: cubic rsqrt + one Goldschmidt correction.
+__device__ __forceinline__ double sqrt_nonneg(double w) {
+  const double y0 = rsqrt_seed(w);
+  const double t = w * y0;
+  const double e = fma(-t, y0, 1.0);
+  const double y1 = fma(fma(e, 0.375, 0.5), e * y0, y0);
+  const double g = w * y1;
+  const double h = 0.5 * y1;
+  const double r = fma(-g, h, 0.5);
+  const double s = fma(g, r, g);
+  return (w <= 2.3e-308) ? 0.0 : s;                        // NaN propagates
+}
+// exp(-s) for s >= 0 (clamped at s = 700: below 1e-304 either way), ~1 ulp, no branches.
+__device__ __forceinline__ double exp_neg(double s) {
+  s = (s > 700.0) ? 700.0 : s;                               // NaN stays NaN
+  const double kShift = 6755399441055744.0;                  // 1.5 * 2^52
+  const double t = fma(-s, 1.4426950408889634, kShift);      // round(-s / ln2) in the low mantissa bits
+  const double kf = t - kShift;
+  double r = fma(kf, -6.93147180369123816490e-01, -s);       // ln2 hi
+  r = fma(kf, -1.90821492927058770002e-10, r);               // ln2 lo
+  double p = GPV_EXP_C11;
+  p = fma(p, r, GPV_EXP_C10);
+  p = fma(p, r, GPV_EXP_C9);
+  p = fma(p, r, GPV_EXP_C8);
+  p = fma(p, r, GPV_EXP_C7);
+  p = fma(p, r, GPV_EXP_C6);
+  p = fma(p, r, GPV_EXP_C5);
+  p = fma(p, r, GPV_EXP_C4);
+  p = fma(p, r, GPV_EXP_C3);
+  p = fma(p, r, GPV_EXP_C2);
+  p = fma(p, r, GPV_EXP_C1);
+  p = fma(p, r, GPV_EXP_C0);
+  const int k = __double2loint(t);                           // -1011 <= k <= 0
+  return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
+}
 
 // --------------------------------------------------------------------------------------------
 // covariance as a function of the SQUARED distance r2 (src/Matern.cpp, src/Esqe.cpp restated;
@@ -84,77 +141,114 @@ __device__ __forceinline__ double cov_general(double r2, const UParams& q);
 
 template <int KIND>
 __device__ __forceinline__ double cov_eval(double r2, const UParams& q) {
-  if (KIND == COV_EXP) {          // Matern.cpp:38-39   sig2 exp(-d/range)          c1 = 1/range
-    return q.c0 * exp(-sqrt(r2) * q.c1);
-  } else if (KIND == COV_M15) {   // :51-52  sig2 (1+sqrt3 s) exp(-sqrt3 s)          c1 = sqrt3/range
-    double t = sqrt(r2) * q.c1;
-    return q.c0 * (1.0 + t) * exp(-t);
-  } else if (KIND == COV_M25) {   // :66-68  sig2 exp(-t)(1 + t + t^2/3), t = sqrt5 s  c1 = sqrt5/range
-    double t = sqrt(r2) * q.c1;
-    return q.c0 * exp(-t) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0);
+  if (KIND == COV_EXP) {          // Matern.cpp:38-39   sig2 exp(-d/range)               c1 = 1/range
+    return q.c0 * exp_neg(sqrt_nonneg(r2) * q.c1);
+  } else if (KIND == COV_M15) {   // :51-52  sig2 (1+sqrt3 s) exp(-sqrt3 s)              c1 = sqrt3/range
+    const double t = sqrt_nonneg(r2) * q.c1;
+    return fma(q.c0, t, q.c0) * exp_neg(t);
+  } else if (KIND == COV_M25) {   // :66-68  sig2 exp(-t)(1 + t + t^2/3), t = sqrt5 s     c1 = sqrt5/range
+    const double t = sqrt_nonneg(r2) * q.c1;
+    return q.c0 * exp_neg(t) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0);
   } else if (KIND == COV_ESQE) {  // Esqe.cpp:32-34  c4 = sig2_1, c1 = 1/r1, c2 = sig2_2, c3 = 1/r2^2
-    return fma(q.c2, exp(-r2 * q.c3), q.c4 * exp(-sqrt(r2) * q.c1));
+    return fma(q.c2, exp_neg(r2 * q.c3), q.c4 * exp_neg(sqrt_nonneg(r2) * q.c1));
   } else {
     return cov_general(r2, q);
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// per-set shared-memory layout
+// --------------------------------------------------------------------------------------------
 template <int G, int P, int D>
-struct GroupLayout {
+struct SetLayout {
   static constexpr int DD = (D > 0) ? D : GPV_MAX_D;
-  static constexpr int LD = (P % 2 == 0) ? P + 1 : P;   // odd leading dimension
-  static constexpr int kL = ((P * LD + 1) / 2) * 2;     // doubles, even => 16B aligned blocks
-  static constexpr int kX = DD * G;                     // SoA coordinate staging
-  static constexpr int kI = G / 2;                      // G int32 ids
-  static constexpr int kDoubles = kL + kX + kI;
+  static constexpr int NLOW = (P + 1) / 2;                 // rows 0..NLOW-1, row q on lane q
+  static constexpr int NHIGH = P / 2;                      // rows P-1..NLOW, row P-1-q on lane q
+  static constexpr int LD = (P % 2 == 0) ? P + 1 : P;      // odd : L(r,c) at c*LD + r
+  static constexpr int LDS = (P % 2 == 0) ? P : P + 1;     // even: staged A(hi,lo) at lo*LDS + hi
+  static constexpr int kBufRaw = (P * LD > P * LDS) ? P * LD : P * LDS;
+  static constexpr int kBuf = ((kBufRaw + 1) / 2) * 2;
+  static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
+  static constexpr int kX = DD * PX;
+  static constexpr int kI = PX / 2;                        // P int32 ids
   static constexpr int kSetsPerWarp = 32 / G;
+  // offset consecutive sets of a warp by 128/kSetsPerWarp bytes (mod 128) so that the per-set
+  // broadcast loads of one warp instruction fall into different banks
+  static constexpr int kRaw = kBuf + kX + kI;
+  static constexpr int kWant = (kSetsPerWarp > 1) ? 16 / kSetsPerWarp : 0;   // doubles, mod 16
+  static constexpr int kPad = (kSetsPerWarp > 1) ? ((kWant - (kRaw % 16)) + 16) % 16 : (kRaw % 2);
+  static constexpr int kDoubles = kRaw + kPad;
   static constexpr int kBytesPerBlock = kDoubles * 8 * kSetsPerWarp * kWarpsPerBlock;
+  static_assert(NLOW <= G, "a lane group must hold ceil(P/2) low rows");
+  static_assert(P >= 2 && P <= 64 && G <= 32, "unsupported set size");
 };
 
-// pair stage: lane gl evaluates the covariances (gl, gl+t mod P), t = 1..P/2
-template <int KIND, int G, int P, int D>
-__device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict__ Ls,
-                                           const double* __restrict__ xs, const double* xi,
-                                           int gl, int npad, int d) {
-  using LY = GroupLayout<G, P, D>;
-  constexpr int LD = LY::LD;
-#pragma unroll 1
-  for (int t = 1; t <= P / 2; ++t) {
-    int j = gl + t;
-    if (j >= P) j -= P;
-    double r2 = 0.0;
-    if (D > 0) {
+template <int D>
+__device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX, const double* xi, int j, int d) {
+  double r2 = 0.0;
+  if (D > 0) {
 #pragma unroll
-      for (int c = 0; c < LY::DD; ++c) {
-        double dd = xi[c] - xs[c * G + j];
+    for (int c = 0; c < D; ++c) {
+      const double dd = xi[c] - xs[c * PX + j];
+      r2 = fma(dd, dd, r2);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < GPV_MAX_D; ++c) {
+      if (c < d) {
+        const double dd = xi[c] - xs[c * PX + j];
         r2 = fma(dd, dd, r2);
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < GPV_MAX_D; ++c) {
-        if (c < d) {
-          double dd = xi[c] - xs[c * G + j];
-          r2 = fma(dd, dd, r2);
-        }
-      }
     }
-    double v = cov_eval<KIND>(r2, q);
-    if (gl < npad || j < npad) v = 0.0;
-    const bool active = (gl < P) && ((2 * t < P) || (gl < P / 2));
-    const int hi = gl > j ? gl : j;
-    const int lo = gl > j ? j : gl;
-    if (active) Ls[hi * LD + lo] = v;
+  }
+  return r2;
+}
+
+// pair stage: point i evaluates the covariances (i, i+t mod P), t = 1..P/2; every lane carries its
+// low point q and its high point P-1-q through the same iteration (two independent chains).
+template <int KIND, int G, int P, int D>
+__device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict__ As,
+                                           const double* __restrict__ xs, const double* xl,
+                                           const double* xh, int gl, int npad, int d) {
+  using LY = SetLayout<G, P, D>;
+  constexpr int LDS = LY::LDS;
+  const bool lowv = gl < LY::NLOW;
+  const bool highv = gl < LY::NHIGH;
+  const int il = lowv ? gl : 0;
+  const int ih = highv ? (P - 1 - gl) : (P - 1);
+#pragma unroll 1
+  for (int t = 1; t <= P / 2; ++t) {
+    int jl = il + t; if (jl >= P) jl -= P;
+    int jh = ih + t; if (jh >= P) jh -= P;
+    const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
+    const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
+    double vl = cov_eval<KIND>(r2l, q);
+    double vh = cov_eval<KIND>(r2h, q);
+    if (il < npad || jl < npad) vl = 0.0;
+    if (ih < npad || jh < npad) vh = 0.0;
+    const bool full = (2 * t < P);                       // even P: t = P/2 pairs are covered by i < P/2 only
+    if (lowv && (full || il < P / 2)) {
+      const int a = il > jl ? il : jl, b = il > jl ? jl : il;
+      As[b * LDS + a] = vl;
+    }
+    if (highv && (full || ih < P / 2)) {
+      const int a = ih > jh ? ih : jh, b = ih > jh ? jh : ih;
+      As[b * LDS + a] = vh;
+    }
   }
 }
 
+// resident blocks per SM the register allocation is sized for (shared memory allows the same)
+template <int P>
+struct Occupancy { static constexpr int kMinBlocks = (P <= 16) ? 4 : (P <= 32) ? 3 : (P <= 41) ? 2 : 1; };
+
 template <int G, int P, int D>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kThreadsPerBlock, Occupancy<P>::kMinBlocks)
 u_sets_kernel(const UParams q) {
-  using LY = GroupLayout<G, P, D>;
-  constexpr int LD = LY::LD;
+  using LY = SetLayout<G, P, D>;
+  constexpr int LD = LY::LD, LDS = LY::LDS, NLOW = LY::NLOW, NHIGH = LY::NHIGH, PX = LY::PX;
   constexpr int SETS = LY::kSetsPerWarp;
   constexpr unsigned FULL = 0xffffffffu;
-  static_assert(P <= G && G <= 32, "set must fit its lane group");
 
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -164,154 +258,205 @@ u_sets_kernel(const UParams q) {
   const int base = sub * G;
   const unsigned gmask = (G == 32) ? FULL : ((1u << G) - 1u);
   const int d = (D > 0) ? D : q.d;
+  const int p = q.p;
 
-  double* Ls = smem + (size_t)(warp * SETS + sub) * LY::kDoubles;
-  double* xs = Ls + LY::kL;
+  double* buf = smem + (size_t)(warp * SETS + sub) * LY::kDoubles;   // staging, then L
+  double* xs = buf + LY::kBuf;
   int* ids = reinterpret_cast<int*>(xs + LY::kX);
 
+  const bool lowv = gl < NLOW;
+  const bool highv = gl < NHIGH;
+  const int rl = lowv ? gl : NLOW - 1;               // clamped row indices keep idle lanes in bounds
+  const int rh = highv ? (P - 1 - gl) : (P - 1);
+
   double acc_quad = 0.0, acc_logd = 0.0;
-  const int p = q.p;
   const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock * SETS;
 
   for (int64_t r0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * SETS; r0 < q.nrows; r0 += stride) {
     const int64_t row = r0 + sub;
     const bool row_ok = row < q.nrows;
 
-    // ---- 1. ids, compaction (U_NZentries.cpp:41-45) ----------------------------------------
-    int raw = -1;
-    if (row_ok && gl < p) raw = q.nn[row * p + gl];
-    const unsigned bal = __ballot_sync(FULL, raw >= 0);
-    const unsigned bits = (bal >> base) & gmask;
-    const int n0 = __popc(bits);
+    // ---- 1. ids, compaction (U_NZentries.cpp:41-45): entries gl and gl + G of the row ---------
+    int raw0 = -1, raw1 = -1;
+    if (row_ok) {
+      const int32_t* nnr = q.nn + row * (int64_t)p;
+      if (gl < p) raw0 = nnr[gl];
+      if (gl + G < p) raw1 = nnr[gl + G];
+    }
+    const unsigned b0 = (__ballot_sync(FULL, raw0 >= 0) >> base) & gmask;
+    const unsigned b1 = (__ballot_sync(FULL, raw1 >= 0) >> base) & gmask;
+    const unsigned anyvalid = __ballot_sync(FULL, (raw0 >= 0) | (raw1 >= 0));
+    if (anyvalid == 0u) continue;                      // warp-uniform: nothing to factor
+    const int n0 = __popc(b0) + __popc(b1);
     const int npad = P - n0;
-    // warp-uniform skip: nothing to factor anywhere in this warp
-    if (bal == 0u) continue;
     {
-      const int rank = __popc(bits & ((1u << gl) - 1u));
+      const unsigned below = (1u << gl) - 1u;
       if (gl < npad) ids[gl] = -1;
+      if (gl + G < npad) ids[gl + G] = -1;
       __syncwarp();
-      if (raw >= 0) ids[npad + rank] = raw;
+      if (raw0 >= 0) ids[npad + __popc(b0 & below)] = raw0;
+      if (raw1 >= 0) ids[npad + __popc(b0) + __popc(b1 & below)] = raw1;
       __syncwarp();
     }
-    const int id = (gl < P) ? ids[gl] : -1;
-    const bool real = id >= 0;
     const uint64_t cmask = row_ok ? q.cond[row] : 0ull;
-    // compacted entry j reads revCond[row, p - n0 + j] (U_NZentries.cpp:47); local index gl = npad + j
-    const int cpos = gl - (P - p);
-    const bool condbit = real && ((cmask >> (cpos & 63)) & 1ull);
 
-    // ---- 2. gather coordinates and nugget ----------------------------------------------------
-    double xi[LY::DD];
-    double diag = 1.0;
-    if (real) {
+    // ---- 2. gather coordinates and nuggets of my two points -------------------------------------
+    double xl[LY::DD], xh[LY::DD];
+    double dgl = 1.0, dgh = 1.0;
+    int idl = -1, idh = -1;
+    bool cl = false, ch = false;
+    if (lowv) idl = ids[rl];
+    if (highv) idh = ids[rh];
+#pragma unroll
+    for (int c = 0; c < LY::DD; ++c) { xl[c] = 0.0; xh[c] = 0.0; }
+    if (idl >= 0) {
       if (D == 2) {
-        const double2 v = reinterpret_cast<const double2*>(q.locs)[id];
-        xi[0] = v.x; xi[1] = v.y;
+        const double2 v = reinterpret_cast<const double2*>(q.locs)[idl];
+        xl[0] = v.x; xl[1] = v.y;
       } else {
 #pragma unroll
-        for (int c = 0; c < LY::DD; ++c) xi[c] = (c < d) ? q.locs[(int64_t)id * d + c] : 0.0;
+        for (int c = 0; c < LY::DD; ++c) if (c < d) xl[c] = q.locs[(int64_t)idl * d + c];
       }
-      // nug = nuggets[id] * (1 - revCond)   (U_NZentries.cpp:47; Inf * 0 = NaN kept on purpose)
-      const double nug = q.nuggets[id] * (1.0 - (condbit ? 1.0 : 0.0));
-      diag = q.c0 + nug;
-    } else {
+      // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
+      cl = (cmask >> ((rl - (P - p)) & 63)) & 1ull;
+      dgl = q.c0 + q.nuggets[idl] * (1.0 - (cl ? 1.0 : 0.0));   // Inf * 0 = NaN kept on purpose
+    }
+    if (idh >= 0) {
+      if (D == 2) {
+        const double2 v = reinterpret_cast<const double2*>(q.locs)[idh];
+        xh[0] = v.x; xh[1] = v.y;
+      } else {
 #pragma unroll
-      for (int c = 0; c < LY::DD; ++c) xi[c] = 0.0;
+        for (int c = 0; c < LY::DD; ++c) if (c < d) xh[c] = q.locs[(int64_t)idh * d + c];
+      }
+      ch = (cmask >> ((rh - (P - p)) & 63)) & 1ull;
+      dgh = q.c0 + q.nuggets[idh] * (1.0 - (ch ? 1.0 : 0.0));
     }
 #pragma unroll
-    for (int c = 0; c < LY::DD; ++c) xs[c * G + gl] = xi[c];
+    for (int c = 0; c < LY::DD; ++c) {
+      if (lowv) xs[c * PX + rl] = xl[c];
+      if (highv) xs[c * PX + rh] = xh[c];
+    }
     __syncwarp();
 
-    // ---- 3. covariance pairs -> shared staging ------------------------------------------------
+    // ---- 3. covariance pairs -> shared staging (column-major lower, even stride) -----------------
     switch (q.cov) {
-      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, Ls, xs, xi, gl, npad, d); break;
-      case COV_M15: pair_stage<COV_M15, G, P, D>(q, Ls, xs, xi, gl, npad, d); break;
-      case COV_M25: pair_stage<COV_M25, G, P, D>(q, Ls, xs, xi, gl, npad, d); break;
-      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, Ls, xs, xi, gl, npad, d); break;
-      default: pair_stage<COV_GENERAL, G, P, D>(q, Ls, xs, xi, gl, npad, d); break;
+      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
+      case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
+      case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
+      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
+      default: pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
     }
-    if (gl < P) Ls[gl * LD + gl] = diag;
+    if (lowv) buf[rl * LDS + rl] = dgl;
+    if (highv) buf[rh * LDS + rh] = dgh;
     __syncwarp();
 
-    // ---- 4. row of the lower triangle into registers -------------------------------------------
-    double a[P];
-    {
-      const int rr = gl < P ? gl : P - 1;
+    // ---- 4. my two rows of the lower triangle into registers ---------------------------------------
+    double lo[NLOW], hi[P];
 #pragma unroll
-      for (int j = 0; j < P; ++j) a[j] = Ls[rr * LD + j];   // j > rr: stale garbage, never used
-    }
+    for (int j = 0; j < NLOW; ++j) lo[j] = buf[j * LDS + rl];     // j > rl: stale, never used
+#pragma unroll
+    for (int j = 0; j < P; ++j) hi[j] = buf[j * LDS + rh];        // j > rh: stale, never used
     __syncwarp();
 
-    // ---- 5. right-looking Cholesky (chol(covmat,"upper"), U_NZentries.cpp:61) --------------------
+    // ---- 5. right-looking Cholesky (chol(covmat,"upper"), U_NZentries.cpp:61) ------------------------
     bool fail = false;
-    double myinv = 0.0;
+    double invl = 0.0, invh = 0.0;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const double akk = __shfl_sync(FULL, a[k], base + k);
-      fail = fail || !(akk > 0.0);          // dpotrf: leading minor not positive definite (or NaN)
-      const double inv = rsqrt(akk);        // rsqrt(+Inf) = 0 : an Inf nugget decouples that neighbour
-      const double l = a[k] * inv;          // lane r >= k: L[r][k]; lane k: sqrt(akk)
-      if (gl == k) myinv = inv;
-      if (gl < P) Ls[k * LD + gl] = l;      // column k of L, contiguous
+      const double akk = (k < NLOW) ? __shfl_sync(FULL, lo[k < NLOW ? k : 0], base + k)
+                                    : __shfl_sync(FULL, hi[k], base + (P - 1 - k));
+      fail = fail || !(akk > 0.0);          // dpotrf: leading minor not positive definite, or NaN
+      const double inv = rsqrt_pos(akk);    // +Inf -> 0 : an Inf nugget decouples that neighbour
+      double ll = 0.0;
+      if (k < NLOW) {
+        ll = lo[k < NLOW ? k : 0] * inv;    // lanes gl >= k: L[gl][k]
+        if (gl == k) invl = inv;
+        if (lowv) buf[k * LD + rl] = ll;
+      } else {
+        if (gl == P - 1 - k) invh = inv;
+      }
+      const double lh = hi[k] * inv;        // lanes with rh >= k: L[rh][k]
+      if (highv) buf[k * LD + rh] = lh;
       __syncwarp();
-      // trailing update of my row: a[j] -= L[r][k] * L[j][k], j = k+1..P-1 (garbage for j > r)
-      constexpr int dummy = 0; (void)dummy;
+      // trailing update: a[r][j] -= L[r][k] * L[j][k], j = k+1..P-1 (garbage beyond the row end)
       int j = k + 1;
-      if (j < P) {                          // (k*LD + j) is odd here: one scalar broadcast load
-        a[j] = fma(-l, Ls[k * LD + j], a[j]);
+      if (j < P) {                          // k*LD + j is odd here: one scalar broadcast load
+        const double l1 = buf[k * LD + j];
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l1, lo[j < NLOW ? j : 0]);
+        hi[j] = fma(-lh, l1, hi[j]);
         ++j;
       }
 #pragma unroll
-      for (; j + 1 < P; j += 2) {           // (k*LD + j) even: 16B broadcast loads
-        const double2 lj = *reinterpret_cast<const double2*>(&Ls[k * LD + j]);
-        a[j] = fma(-l, lj.x, a[j]);
-        a[j + 1] = fma(-l, lj.y, a[j + 1]);
+      for (; j + 1 < P; j += 2) {           // k*LD + j even: 16-byte broadcast loads
+        const double2 l2 = *reinterpret_cast<const double2*>(&buf[k * LD + j]);
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l2.x, lo[j < NLOW ? j : 0]);
+        if (j + 1 < NLOW) lo[j + 1 < NLOW ? j + 1 : 0] = fma(-ll, l2.y, lo[j + 1 < NLOW ? j + 1 : 0]);
+        hi[j] = fma(-lh, l2.x, hi[j]);
+        hi[j + 1] = fma(-lh, l2.y, hi[j + 1]);
       }
-      if (j < P) a[j] = fma(-l, Ls[k * LD + j], a[j]);
+      if (j < P) {
+        const double l1 = buf[k * LD + j];
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l1, lo[j < NLOW ? j : 0]);
+        hi[j] = fma(-lh, l1, hi[j]);
+      }
     }
 
-    // ---- 6. x = L^{-T} e_P  (solve(R, onevec), U_NZentries.cpp:62) --------------------------------
-    double s = 0.0;
-    double x = 0.0;
+    // ---- 6. x = L^{-T} e_P  (solve(R, onevec), U_NZentries.cpp:62): column sweep, j = P-1..1 ---------
+    double sl = 0.0, sh = 0.0, xlow = 0.0, xhigh = 0.0;
 #pragma unroll
     for (int j = P - 1; j >= 1; --j) {
-      const double cand = (j == P - 1) ? myinv : -s * myinv;   // x_j on lane j
-      const double xj = __shfl_sync(FULL, cand, base + j);
-      if (gl == j) x = xj;
-      const int rr = gl < j ? gl : 0;
-      const double lji = Ls[rr * LD + j];                      // L[j][gl]
-      if (gl < j) s = fma(lji, xj, s);
+      double xj;
+      if (j >= NLOW) {                       // x_j lives on lane P-1-j (high row)
+        const double cand = (j == P - 1) ? invh : -sh * invh;
+        xj = __shfl_sync(FULL, cand, base + (P - 1 - j));
+        if (gl == P - 1 - j) xhigh = xj;
+      } else {                               // x_j lives on lane j (low row)
+        xj = __shfl_sync(FULL, -sl * invl, base + j);
+        if (gl == j) xlow = xj;
+      }
+      // s_r += L[j][r] * x_j for r < j ; L[j][r] sits at buf[r*LD + j]
+      if (rl < j) sl = fma(buf[rl * LD + j], xj, sl);
+      if (j > NLOW && rh < j) sh = fma(buf[rh * LD + j], xj, sh);
     }
-    if (gl == 0) x = (P == 1) ? myinv : -s * myinv;
-    if (fail) x = 0.0;                                         // row stays zero (:64-66)
+    if (gl == 0) xlow = -sl * invl;          // x_0
+    if (fail) { xlow = 0.0; xhigh = 0.0; }   // row stays zero (:64-66)
 
-    // ---- 7. outputs ---------------------------------------------------------------------------------
+    // ---- 7. outputs ----------------------------------------------------------------------------------
     if (fail && row_ok && gl == 0 && n0 > 0) {
       atomicAdd(q.nfail, 1ull);
       atomicMin(q.first_fail, (long long)(q.row0 + row));
     }
     if (q.out != nullptr && row_ok) {
       if (q.row_off != nullptr) {
-        if (real) q.out[q.row_off[row] + (gl - npad)] = x;
+        double* o = q.out + q.row_off[row];
+        if (idl >= 0) o[rl - npad] = xlow;
+        if (idh >= 0) o[rh - npad] = xhigh;
       } else {
         double* o = q.out + row * (int64_t)p;
-        if (real) o[gl - npad] = x;
-        else if (gl < P && n0 + gl < p) o[n0 + gl] = 0.0;     // zero fill beyond n0 (:33)
+        if (idl >= 0) o[rl - npad] = xlow;
+        if (idh >= 0) o[rh - npad] = xhigh;
+        if (gl >= n0 && gl < p) o[gl] = 0.0;             // zero fill beyond n0 (:33)
+        if (gl + G >= n0 && gl + G < p) o[gl + G] = 0.0;
       }
     }
     if (q.partials != nullptr) {
       // quadform: (sum_{j: revCond = 0} x_j * zord[obsrank(id_j)])^2 ; logdet: log x_self
       double t = 0.0;
-      if (real && !condbit) {
-        const int orank = q.obsrank[id];
-        if (orank >= 0) t = x * q.zord[orank];
+      if (idl >= 0 && !cl) {
+        const int orank = q.obsrank[idl];
+        if (orank >= 0) t = xlow * q.zord[orank];
+      }
+      if (idh >= 0 && !ch) {
+        const int orank = q.obsrank[idh];
+        if (orank >= 0) t = fma(xhigh, q.zord[orank], t);
       }
 #pragma unroll
       for (int o = G / 2; o >= 1; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-      const double xs_self = __shfl_sync(FULL, x, base + P - 1);
+      const double xself = __shfl_sync(FULL, xhigh, base);     // row P-1 is lane 0's high row
       if (gl == 0 && row_ok && n0 > 0 && (q.row0 + row) >= q.skip_rows) {
         acc_quad += t * t;
-        acc_logd += log(xs_self);
+        acc_logd += log(xself);
       }
     }
     __syncwarp();
