@@ -45,44 +45,71 @@ def bytes_per_set(p, d):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML through
+    pynvml (~1 ms per sample), falling back to the nvidia-smi query of the profiling recipe."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.max_sm, self.power = [], set(), None, []
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+        except Exception:
+            pass
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        self.sm.append(float(r[0]))
+        self.max_sm = max(self.max_sm or 0.0, float(r[1]))
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.002 if self._nvml is not None else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
-                    reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.max_sm,
+                    reasons=sorted(self.reasons), samples=len(self.sm),
+                    power_w_max=max(self.power) if self.power else None,
+                    source="nvml" if self._nvml is not None else "nvidia-smi")
 
 
 def make_inputs(n_total, row_begin, row_end, device, use_gpu_nn=True):
@@ -128,7 +155,7 @@ def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covpa
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)

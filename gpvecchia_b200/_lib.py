@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpvecchia_b200.so")
+# GPV_LIB_PATH: development override used by tools/kbench.py to compare kernel variants
+LIB_PATH = os.environ.get("GPV_LIB_PATH") or os.path.join(_HERE, "libgpvecchia_b200.so")
 
 GPV_OK = 0
 GPV_ERR_ARG, GPV_ERR_CUDA, GPV_ERR_COVTYPE, GPV_ERR_NOMEM, GPV_ERR_UNSUPPORTED = 1, 2, 3, 4, 5

@@ -26,7 +26,7 @@ constexpr int kTabDeg = 10;
 constexpr int kTabSubBits = 4;              // 16 intervals per octave of w
 constexpr int kTabSub = 1 << kTabSubBits;
 constexpr int kTabOctaves = 64;             // covered range of w below its maximum
-constexpr double kTabSSplit = 1.0;          // s >= split: table holds exp(s) * cov
+constexpr double kTabSSplit = 16.0;          // s >= split: table holds exp(s) * cov
 
 __host__ __device__ inline int hi32_of(double x) {
 #ifdef __CUDA_ARCH__

@@ -78,26 +78,66 @@ constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
 // --------------------------------------------------------------------------------------------
 // branch-free fp64 primitives
 // --------------------------------------------------------------------------------------------
+// Polynomial / reduction constants live in constant memory so DFMA takes them as c[bank][offset]
+// operands; as literals ptxas re-materialised them with two UMOVs each inside the pair loop
+// (8% of all issued instructions in the first profile, profiles/r01_*).
+__constant__ double kMathC[16] = {
+    GPV_EXP_C0, GPV_EXP_C1, GPV_EXP_C2, GPV_EXP_C3, GPV_EXP_C4, GPV_EXP_C5, GPV_EXP_C6, GPV_EXP_C7,
+    GPV_EXP_C8, GPV_EXP_C9, GPV_EXP_C10, GPV_EXP_C11,
+    1.4426950408889634,            // [12] log2(e)
+    -6.93147180369123816490e-01,   // [13] -ln2 hi
+    -1.90821492927058770002e-10,   // [14] -ln2 lo
+    1.0e-300};                     // [15] sqrt guard
+
+#ifndef GPV_MINB32
+#define GPV_MINB32 4
+#endif
+#ifndef GPV_EXP_ESTRIN
+#define GPV_EXP_ESTRIN 0
+#endif
+#ifndef GPV_RSQRT_NEWTON
+#define GPV_RSQRT_NEWTON 0
+#endif
+#ifndef GPV_PAIR_UNROLL
+#define GPV_PAIR_UNROLL 1
+#endif
+
 __device__ __forceinline__ double rsqrt_seed(double a) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, ~20 good bits
   return y;
 }
-// 1/sqrt(a) for finite normal a > 0 to ~1 ulp: cubic step then a Newton step.
-// a = +Inf returns +0 (seed is +0, refinement is skipped by the select); a <= 0 / NaN: garbage,
-// callers test `a > 0` themselves.
+// 1/sqrt(a) for finite normal a > 0 to ~1 ulp: cubic step (+ a Newton step).
+// a = +Inf returns +0; a <= 0 / NaN: garbage, callers test `a > 0` themselves.
 __device__ __forceinline__ double rsqrt_pos(double a) {
   const double y0 = rsqrt_seed(a);
   const double t = a * y0;
   const double e = fma(-t, y0, 1.0);
-  const double y1 = fma(fma(e, 0.375, 0.5), e * y0, y0);     // error ~ e^3
-  const double t1 = a * y1;
-  const double e1 = fma(-t1, y1, 1.0);
-  const double y2 = fma(0.5 * e1, y1, y1);
-  return (a < 1.7976931348623157e308) ? y2 : 0.0;
+  double y = fma(fma(e, 0.375, 0.5), e * y0, y0);            // error ~ e^3
+  const double t1 = a * y;                                   // once per set: keep the Newton step
+  const double e1 = fma(-t1, y, 1.0);
+  y = fma(0.5 * e1, y, y);
+  return (a < 1.7976931348623157e308) ? y : 0.0;
 }
-// sqrt(w) for w >= 0 (w == 0 or denormal -> 0) to ~1 ulp: cubic rsqrt + one Goldschmidt correction.
+// 1/a for finite normal a > 0 to ~1 ulp (cubic step from the MUFU.RCP64H seed, + optional Newton
+// step); a = +Inf returns +0; a <= 0 / NaN: garbage, callers test `a > 0` themselves.
+__device__ __forceinline__ double rcp_pos(double a) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+  const double e = fma(-a, y0, 1.0);
+  double y = fma(fma(e, e, e), y0, y0);                      // y0 (1 + e + e^2): error ~ e^3
+#if GPV_RSQRT_NEWTON
+  const double e1 = fma(-a, y, 1.0);
+  y = fma(y, e1, y);
+#endif
+  return (a < 1.7976931348623157e308) ? y : 0.0;
+}
+// sqrt(w) for w >= 0 to ~1 ulp: cubic rsqrt + one Goldschmidt correction.  The 1e-300 guard keeps
+// w == 0 (duplicate locations) away from rsqrt(0) = Inf without a select: sqrt(1e-300) = 1e-150
+// rounds away in every use (exp(-1e-150 c) == 1, 1 + 1e-150 c == 1), so r2 == 0 still returns
+// exactly c0 like the reference's `dist == 0` branches; NaN propagates.
 __device__ __forceinline__ double sqrt_nonneg(double w) {
+  w += kMathC[15];
   const double y0 = rsqrt_seed(w);
   const double t = w * y0;
   const double e = fma(-t, y0, 1.0);
@@ -105,29 +145,40 @@ __device__ __forceinline__ double sqrt_nonneg(double w) {
   const double g = w * y1;
   const double h = 0.5 * y1;
   const double r = fma(-g, h, 0.5);
-  const double s = fma(g, r, g);
-  return (w <= 2.3e-308) ? 0.0 : s;                        // NaN propagates
+  return fma(g, r, g);
 }
 // exp(-s) for s >= 0 (clamped at s = 700: below 1e-304 either way), ~1 ulp, no branches.
 __device__ __forceinline__ double exp_neg(double s) {
   s = (s > 700.0) ? 700.0 : s;                               // NaN stays NaN
   const double kShift = 6755399441055744.0;                  // 1.5 * 2^52
-  const double t = fma(-s, 1.4426950408889634, kShift);      // round(-s / ln2) in the low mantissa bits
+  const double t = fma(-s, kMathC[12], kShift);              // round(-s / ln2) in the low mantissa bits
   const double kf = t - kShift;
-  double r = fma(kf, -6.93147180369123816490e-01, -s);       // ln2 hi
-  r = fma(kf, -1.90821492927058770002e-10, r);               // ln2 lo
-  double p = GPV_EXP_C11;
-  p = fma(p, r, GPV_EXP_C10);
-  p = fma(p, r, GPV_EXP_C9);
-  p = fma(p, r, GPV_EXP_C8);
-  p = fma(p, r, GPV_EXP_C7);
-  p = fma(p, r, GPV_EXP_C6);
-  p = fma(p, r, GPV_EXP_C5);
-  p = fma(p, r, GPV_EXP_C4);
-  p = fma(p, r, GPV_EXP_C3);
-  p = fma(p, r, GPV_EXP_C2);
-  p = fma(p, r, GPV_EXP_C1);
-  p = fma(p, r, GPV_EXP_C0);
+  double r = fma(kf, kMathC[13], -s);
+  r = fma(kf, kMathC[14], r);
+#if GPV_EXP_ESTRIN
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = 1.0 + r;
+  const double a1 = fma(kMathC[3], r, kMathC[2]);
+  const double a2 = fma(kMathC[5], r, kMathC[4]);
+  const double a3 = fma(kMathC[7], r, kMathC[6]);
+  const double a4 = fma(kMathC[9], r, kMathC[8]);
+  const double a5 = fma(kMathC[11], r, kMathC[10]);
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double p = fma(b2, r8, fma(b1, r4, b0));
+#else
+  double p = kMathC[11];
+  p = fma(p, r, kMathC[10]);
+  p = fma(p, r, kMathC[9]);
+  p = fma(p, r, kMathC[8]);
+  p = fma(p, r, kMathC[7]);
+  p = fma(p, r, kMathC[6]);
+  p = fma(p, r, kMathC[5]);
+  p = fma(p, r, kMathC[4]);
+  p = fma(p, r, kMathC[3]);
+  p = fma(p, r, kMathC[2]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+#endif
   const int k = __double2loint(t);                           // -1011 <= k <= 0
   return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
 }
@@ -159,15 +210,18 @@ __device__ __forceinline__ double cov_eval(double r2, const UParams& q) {
 // --------------------------------------------------------------------------------------------
 // per-set shared-memory layout
 // --------------------------------------------------------------------------------------------
+// Packed lower triangle, column-major: column k holds rows k..P-1 at tri_col(k) + (r - k).  Used both
+// for the staged covariance matrix and, column by column, for L (a column of L overwrites the
+// staged column it was computed from, which is dead by then).  496 doubles for P = 31 instead of
+// the 992 of a square buffer: shared memory no longer caps residency below the register limit.
+__host__ __device__ constexpr int tri_col(int k, int P) { return k * P - (k * (k - 1)) / 2; }
+
 template <int G, int P, int D>
 struct SetLayout {
   static constexpr int DD = (D > 0) ? D : GPV_MAX_D;
   static constexpr int NLOW = (P + 1) / 2;                 // rows 0..NLOW-1, row q on lane q
   static constexpr int NHIGH = P / 2;                      // rows P-1..NLOW, row P-1-q on lane q
-  static constexpr int LD = (P % 2 == 0) ? P + 1 : P;      // odd : L(r,c) at c*LD + r
-  static constexpr int LDS = (P % 2 == 0) ? P : P + 1;     // even: staged A(hi,lo) at lo*LDS + hi
-  static constexpr int kBufRaw = (P * LD > P * LDS) ? P * LD : P * LDS;
-  static constexpr int kBuf = ((kBufRaw + 1) / 2) * 2;
+  static constexpr int kBuf = ((tri_col(P, P) + 1) / 2) * 2;
   static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
   static constexpr int kX = DD * PX;
   static constexpr int kI = PX / 2;                        // P int32 ids
@@ -205,48 +259,63 @@ __device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX,
 }
 
 // pair stage: point i evaluates the covariances (i, i+t mod P), t = 1..P/2; every lane carries its
-// low point q and its high point P-1-q through the same iteration (two independent chains).
+// low point q and its high point P-1-q through the same iteration (independent chains for ILP).
+// Entries that involve padding are computed on dummy coordinates here and zeroed afterwards
+// (zero_pad_columns): only the first m rows of a data set have padding.
+template <int KIND, int G, int P, int D>
+__device__ __forceinline__ void pair_eval_store(const UParams& q, double* __restrict__ As,
+                                                const double* __restrict__ xs, const double* xl,
+                                                const double* xh, int il, int ih, bool lowv,
+                                                bool highv, int t, int d) {
+  using LY = SetLayout<G, P, D>;
+  int jl = il + t; if (jl >= P) jl -= P;
+  int jh = ih + t; if (jh >= P) jh -= P;
+  const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
+  const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
+  const double vl = cov_eval<KIND>(r2l, q);
+  const double vh = cov_eval<KIND>(r2h, q);
+  const bool full = (2 * t < P);                         // even P: t = P/2 is covered by i < P/2 only
+  if (lowv && (full || il < P / 2)) {
+    const int a = il > jl ? il : jl, b = il > jl ? jl : il;
+    As[tri_col(b, P) + a - b] = vl;
+  }
+  if (highv && (full || ih < P / 2)) {
+    const int a = ih > jh ? ih : jh, b = ih > jh ? jh : ih;
+    As[tri_col(b, P) + a - b] = vh;
+  }
+}
+
 template <int KIND, int G, int P, int D>
 __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict__ As,
                                            const double* __restrict__ xs, const double* xl,
-                                           const double* xh, int gl, int npad, int d) {
+                                           const double* xh, int gl, int d) {
   using LY = SetLayout<G, P, D>;
-  constexpr int LDS = LY::LDS;
   const bool lowv = gl < LY::NLOW;
   const bool highv = gl < LY::NHIGH;
   const int il = lowv ? gl : 0;
   const int ih = highv ? (P - 1 - gl) : (P - 1);
+  constexpr int T = P / 2;
+  int t = 1;
+#if GPV_PAIR_UNROLL == 2
 #pragma unroll 1
-  for (int t = 1; t <= P / 2; ++t) {
-    int jl = il + t; if (jl >= P) jl -= P;
-    int jh = ih + t; if (jh >= P) jh -= P;
-    const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
-    const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
-    double vl = cov_eval<KIND>(r2l, q);
-    double vh = cov_eval<KIND>(r2h, q);
-    if (il < npad || jl < npad) vl = 0.0;
-    if (ih < npad || jh < npad) vh = 0.0;
-    const bool full = (2 * t < P);                       // even P: t = P/2 pairs are covered by i < P/2 only
-    if (lowv && (full || il < P / 2)) {
-      const int a = il > jl ? il : jl, b = il > jl ? jl : il;
-      As[b * LDS + a] = vl;
-    }
-    if (highv && (full || ih < P / 2)) {
-      const int a = ih > jh ? ih : jh, b = ih > jh ? jh : ih;
-      As[b * LDS + a] = vh;
-    }
+  for (; t + 1 <= T; t += 2) {
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t, d);
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t + 1, d);
   }
+#endif
+#pragma unroll 1
+  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t, d);
 }
 
 // resident blocks per SM the register allocation is sized for (shared memory allows the same)
 template <int P>
-struct Occupancy { static constexpr int kMinBlocks = (P <= 16) ? 4 : (P <= 32) ? 3 : (P <= 41) ? 2 : 1; };
+struct Occupancy { static constexpr int kMinBlocks = (P <= 16) ? 4 : (P <= 32) ? GPV_MINB32 : (P <= 41) ? 2 : 1; };
 
 template <int G, int P, int D>
 __global__ void __launch_bounds__(kThreadsPerBlock, Occupancy<P>::kMinBlocks)
 u_sets_kernel(const UParams q) {
   using LY = SetLayout<G, P, D>;
-  constexpr int LD = LY::LD, LDS = LY::LDS, NLOW = LY::NLOW, NHIGH = LY::NHIGH, PX = LY::PX;
+  constexpr int NLOW = LY::NLOW, NHIGH = LY::NHIGH, PX = LY::PX;
   constexpr int SETS = LY::kSetsPerWarp;
   constexpr unsigned FULL = 0xffffffffu;
 
@@ -341,85 +410,97 @@ u_sets_kernel(const UParams q) {
 
     // ---- 3. covariance pairs -> shared staging (column-major lower, even stride) -----------------
     switch (q.cov) {
-      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
-      case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
-      case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
-      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
-      default: pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, npad, d); break;
+      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
+      case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
+      case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
+      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
+      default: pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
     }
-    if (lowv) buf[rl * LDS + rl] = dgl;
-    if (highv) buf[rh * LDS + rh] = dgh;
+    if (__any_sync(FULL, npad > 0)) {
+      // padding occupies the leading indices: every pair with a padded point has its smaller index
+      // < npad, i.e. lives in columns 0..npad-1 of the staged lower triangle -> zero those columns
+      __syncwarp();
+      for (int j = 0; j < npad; ++j) {
+        if (lowv && rl > j) buf[tri_col(j, P) + rl - j] = 0.0;
+        if (highv && rh > j) buf[tri_col(j, P) + rh - j] = 0.0;
+      }
+    }
+    if (lowv) buf[tri_col(rl, P)] = dgl;
+    if (highv) buf[tri_col(rh, P)] = dgh;
     __syncwarp();
 
     // ---- 4. my two rows of the lower triangle into registers ---------------------------------------
     double lo[NLOW], hi[P];
 #pragma unroll
-    for (int j = 0; j < NLOW; ++j) lo[j] = buf[j * LDS + rl];     // j > rl: stale, never used
+    for (int j = 0; j < NLOW; ++j) lo[j] = buf[tri_col(j, P) + rl - j];   // j > rl: stale, never used
 #pragma unroll
-    for (int j = 0; j < P; ++j) hi[j] = buf[j * LDS + rh];        // j > rh: stale, never used
+    for (int j = 0; j < P; ++j) hi[j] = buf[tri_col(j, P) + rh - j];      // j > rh: stale, never used
     __syncwarp();
 
-    // ---- 5. right-looking Cholesky (chol(covmat,"upper"), U_NZentries.cpp:61) ------------------------
+    // ---- 5. right-looking LDL^T (square-root-free Cholesky; chol(covmat,"upper"), U_NZentries.cpp:61)
+    // Sigma = L D L^T with unit lower L.  Column k is published to shared memory already divided by
+    // the pivot (w[j] = a[j][k] / d_k = L[j][k]); every lane keeps its own UNSCALED entry c = a[r][k]
+    // and updates a[r][j] -= c * w[j].  The reference's factor is R = D^{1/2} L^T, so its
+    // R^{-1} e_P = L^{-T} e_P / sqrt(d_P): one rsqrt per set instead of one per pivot, and a
+    // unit-triangular column sweep.  A pivot that is not > 0 (or NaN) is dpotrf's failure.
     bool fail = false;
-    double invl = 0.0, invh = 0.0;
+    double dlast = 1.0;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       const double akk = (k < NLOW) ? __shfl_sync(FULL, lo[k < NLOW ? k : 0], base + k)
                                     : __shfl_sync(FULL, hi[k], base + (P - 1 - k));
-      fail = fail || !(akk > 0.0);          // dpotrf: leading minor not positive definite, or NaN
-      const double inv = rsqrt_pos(akk);    // +Inf -> 0 : an Inf nugget decouples that neighbour
-      double ll = 0.0;
+      fail = fail || !(akk > 0.0);
+      if (k == P - 1) { dlast = akk; break; }
+      const double inv = rcp_pos(akk);      // +Inf -> 0 : an Inf nugget decouples that neighbour
+      // publish L[r][k] = a[r][k] / d_k for r >= k (a packed column must not be written above its top)
+      const int ck = tri_col(k, P) - k;     // L[r][k] at buf[ck + r]
+      double cl = 0.0;
       if (k < NLOW) {
-        ll = lo[k < NLOW ? k : 0] * inv;    // lanes gl >= k: L[gl][k]
-        if (gl == k) invl = inv;
-        if (lowv) buf[k * LD + rl] = ll;
-      } else {
-        if (gl == P - 1 - k) invh = inv;
+        cl = lo[k < NLOW ? k : 0];          // lanes gl >= k: a[gl][k]
+        if (gl >= k && lowv) buf[ck + rl] = cl * inv;
       }
-      const double lh = hi[k] * inv;        // lanes with rh >= k: L[rh][k]
-      if (highv) buf[k * LD + rh] = lh;
+      const double chh = hi[k];             // lanes with rh >= k: a[rh][k]
+      if (gl <= P - 1 - k && highv) buf[ck + rh] = chh * inv;
       __syncwarp();
-      // trailing update: a[r][j] -= L[r][k] * L[j][k], j = k+1..P-1 (garbage beyond the row end)
+      // trailing update: a[r][j] -= a[r][k] * L[j][k], j = k+1..P-1 (garbage beyond the row end)
       int j = k + 1;
-      if (j < P) {                          // k*LD + j is odd here: one scalar broadcast load
-        const double l1 = buf[k * LD + j];
-        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l1, lo[j < NLOW ? j : 0]);
-        hi[j] = fma(-lh, l1, hi[j]);
+      if (j < P && ((ck + j) & 1) != 0) {   // odd offset: one scalar broadcast load first
+        const double l1 = buf[ck + j];
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-cl, l1, lo[j < NLOW ? j : 0]);
+        hi[j] = fma(-chh, l1, hi[j]);
         ++j;
       }
 #pragma unroll
-      for (; j + 1 < P; j += 2) {           // k*LD + j even: 16-byte broadcast loads
-        const double2 l2 = *reinterpret_cast<const double2*>(&buf[k * LD + j]);
-        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l2.x, lo[j < NLOW ? j : 0]);
-        if (j + 1 < NLOW) lo[j + 1 < NLOW ? j + 1 : 0] = fma(-ll, l2.y, lo[j + 1 < NLOW ? j + 1 : 0]);
-        hi[j] = fma(-lh, l2.x, hi[j]);
-        hi[j + 1] = fma(-lh, l2.y, hi[j + 1]);
+      for (; j + 1 < P; j += 2) {           // 16-byte aligned broadcast loads for (j, j+1)
+        const double2 l2 = *reinterpret_cast<const double2*>(&buf[ck + j]);
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-cl, l2.x, lo[j < NLOW ? j : 0]);
+        if (j + 1 < NLOW) lo[j + 1 < NLOW ? j + 1 : 0] = fma(-cl, l2.y, lo[j + 1 < NLOW ? j + 1 : 0]);
+        hi[j] = fma(-chh, l2.x, hi[j]);
+        hi[j + 1] = fma(-chh, l2.y, hi[j + 1]);
       }
       if (j < P) {
-        const double l1 = buf[k * LD + j];
-        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-ll, l1, lo[j < NLOW ? j : 0]);
-        hi[j] = fma(-lh, l1, hi[j]);
+        const double l1 = buf[ck + j];
+        if (j < NLOW) lo[j < NLOW ? j : 0] = fma(-cl, l1, lo[j < NLOW ? j : 0]);
+        hi[j] = fma(-chh, l1, hi[j]);
       }
     }
 
-    // ---- 6. x = L^{-T} e_P  (solve(R, onevec), U_NZentries.cpp:62): column sweep, j = P-1..1 ---------
-    double sl = 0.0, sh = 0.0, xlow = 0.0, xhigh = 0.0;
+    // ---- 6. x = L^{-T} e_P / sqrt(d_P)  (solve(R, onevec), U_NZentries.cpp:62): unit-triangular column
+    // sweep, j = P-1..1.  s_r accumulates sum_{j > r} L[j][r] y_j with y_r = -s_r; the unit right-hand
+    // side enters as s_{P-1} = -1 (row P-1 is lane 0's high row and is never updated below).
+    double sl = 0.0, sh = (gl == 0) ? -1.0 : 0.0;
+    const int cbl = tri_col(rl, P) - rl, cbh = tri_col(rh, P) - rh;
 #pragma unroll
     for (int j = P - 1; j >= 1; --j) {
-      double xj;
-      if (j >= NLOW) {                       // x_j lives on lane P-1-j (high row)
-        const double cand = (j == P - 1) ? invh : -sh * invh;
-        xj = __shfl_sync(FULL, cand, base + (P - 1 - j));
-        if (gl == P - 1 - j) xhigh = xj;
-      } else {                               // x_j lives on lane j (low row)
-        xj = __shfl_sync(FULL, -sl * invl, base + j);
-        if (gl == j) xlow = xj;
-      }
-      // s_r += L[j][r] * x_j for r < j ; L[j][r] sits at buf[r*LD + j]
-      if (rl < j) sl = fma(buf[rl * LD + j], xj, sl);
-      if (j > NLOW && rh < j) sh = fma(buf[rh * LD + j], xj, sh);
+      const double yj = (j >= NLOW) ? __shfl_sync(FULL, -sh, base + (P - 1 - j))
+                                    : __shfl_sync(FULL, -sl, base + j);
+      // L[j][r] sits at buf[tri_col(r) - r + j]
+      if (rl < j) sl = fma(buf[cbl + j], yj, sl);
+      if (j > NLOW && rh < j) sh = fma(buf[cbh + j], yj, sh);
     }
-    if (gl == 0) xlow = -sl * invl;          // x_0
+    const double rs = rsqrt_pos(dlast);
+    double xlow = -sl * rs;
+    double xhigh = -sh * rs;
     if (fail) { xlow = 0.0; xhigh = 0.0; }   // row stays zero (:64-66)
 
     // ---- 7. outputs ----------------------------------------------------------------------------------
