@@ -421,3 +421,42 @@ def exact_loglik(z, locs, covparms, nuggets, covmodel="matern"):
     L = np.linalg.cholesky(S)
     a = np.linalg.solve(L, np.asarray(z, dtype=np.float64))
     return float(-0.5 * (a @ a) - np.log(np.diag(L)).sum() - 0.5 * n * np.log(2 * np.pi))
+
+
+# ----------------------------------------------------------------------------------------------
+# per-row ("fused") form of the numerator, SURVEY.md 8(a10): what the CUDA kernel accumulates.
+# quadform.num = sum_i z_i^2/tau_i + sum_k ( sum_{j: revCond_kj = 0} x_kj * zord[obsrank(id_kj)] )^2
+# logdet.num   = -2 sum_k log x_{k,n0} + sum_i log tau_i ; rows < skip_rows (zy dummies) excluded.
+# ----------------------------------------------------------------------------------------------
+def loglik_numerator_rows(Lentries, revNNarray, revCond, obs, zord, nuggets_ord, row_begin=0,
+                          row_end=None, skip_rows=0, include_obs_terms=True):
+    revNNarray = np.asarray(revNNarray)
+    N, p = revNNarray.shape
+    row_end = N if row_end is None else row_end
+    obs = np.asarray(obs, dtype=bool)
+    obsrank = np.cumsum(obs) - 1
+    quad = 0.0
+    logd = 0.0
+    for k in range(max(row_begin, 0), row_end):
+        ids = revNNarray[k]
+        keep = ids != NA
+        n0 = int(keep.sum())
+        if n0 == 0:
+            continue
+        x = np.asarray(Lentries[k - row_begin])[:n0]
+        cond = revCond[k, p - n0:] == 1              # last n0 columns (U_NZentries.cpp:47)
+        idk = ids[keep] - 1
+        if k < skip_rows:
+            continue
+        t = 0.0
+        for j in range(n0):
+            if not cond[j] and obs[idk[j]]:
+                t += x[j] * zord[obsrank[idk[j]]]
+        quad += t * t
+        with np.errstate(divide="ignore"):
+            logd += np.log(x[n0 - 1])
+    logdet = -2.0 * logd
+    if include_obs_terms:
+        quad += float(np.sum(np.asarray(zord) ** 2 / np.asarray(nuggets_ord)))
+        logdet += float(np.sum(np.log(np.asarray(nuggets_ord))))
+    return quad, logdet

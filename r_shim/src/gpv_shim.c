@@ -1,0 +1,146 @@
+/* gpv_shim.c -- the `.Call` side of the drop-in boundary, for a GPvecchia maintainer.
+ *
+ * Registers routines with the SAME argument lists the reference's generated glue has
+ * (src/RcppExports.cpp:49-67, R/RcppExports.R:22-24) but without Rcpp/Armadillo: it reads the
+ * R vectors in place (INTEGER()/REAL()/LOGICAL()), allocates results with Rf_allocMatrix (owned by
+ * R's GC) and calls the C ABI of include/gpvecchia_b200.h.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no R here (no R.h / Rinternals.h).  The same
+ * C ABI is exercised by gpvecchia_b200/host.py through ctypes.  Build inside the R package with
+ *     PKG_LIBS = -L$(GPV_B200_HOME) -lgpvecchia_b200 -Wl,-rpath,$(GPV_B200_HOME)
+ *     PKG_CPPFLAGS = -I$(GPV_B200_HOME)/include
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include "gpvecchia_b200.h"
+
+static void check(gpv_status st) {
+  /* no device work or host allocation is pending here: the C ABI is synchronous and frees its
+   * own temporaries before returning, so Rf_error's longjmp is safe. */
+  if (st != GPV_OK) Rf_error("gpvecchia_b200: %s", gpv_last_error());
+}
+
+static void warn_fail(int64_t nfail, int64_t first_fail) {
+  if (nfail > 0)
+    Rf_warning("Cholesky decomposition failed for %lld conditioning set(s) (first at row %lld); "
+               "those rows of U are zero", (long long)nfail, (long long)first_fail + 1);
+}
+
+static int device_from_option(void) {
+  SEXP opt = Rf_GetOption1(Rf_install("GPvecchia.b200.device"));
+  return (opt == R_NilValue) ? 0 : Rf_asInteger(opt);
+}
+
+/* ---- stateless drop-in: same nine arguments, same return value as U_NZentries --------------- */
+SEXP gpvb200_U_NZentries(SEXP Ncores, SEXP n, SEXP locs, SEXP revNNarray, SEXP revCondOnLatent,
+                         SEXP nuggets, SEXP nuggets_obsord, SEXP covType, SEXP covparms) {
+  if (!Rf_isMatrix(locs) || !Rf_isReal(locs)) Rf_error("locs must be a numeric matrix");
+  if (!Rf_isMatrix(revNNarray)) Rf_error("revNNarray must be a matrix");
+  const int64_t N = Rf_nrows(locs);
+  const int d = Rf_ncols(locs), p = Rf_ncols(revNNarray);
+  const int64_t nobs = (int64_t)Rf_asReal(n);
+  SEXP nn = PROTECT(Rf_coerceVector(revNNarray, INTSXP));    /* createU.R:146-147 already set NA -> 0 */
+  const int is_lgl = Rf_isLogical(revCondOnLatent);
+  SEXP rc = PROTECT(is_lgl ? revCondOnLatent : Rf_coerceVector(revCondOnLatent, REALSXP));
+  SEXP L = PROTECT(Rf_allocMatrix(REALSXP, (int)N, p));
+  SEXP Z = PROTECT(Rf_allocMatrix(REALSXP, (int)(2 * nobs), 1));
+  int64_t nfail = 0, first = -1;
+  gpv_status st = gpv_U_NZentries(Rf_asInteger(Ncores), nobs, N, p, d, REAL(locs), INTEGER(nn),
+                                  is_lgl ? (const void*)LOGICAL(rc) : (const void*)REAL(rc),
+                                  is_lgl ? GPV_COND_RLOGICAL_I32 : GPV_COND_F64, REAL(nuggets),
+                                  REAL(nuggets_obsord), CHAR(STRING_ELT(covType, 0)), REAL(covparms),
+                                  LENGTH(covparms), REAL(L), REAL(Z), &nfail, &first,
+                                  device_from_option());
+  check(st);
+  warn_fail(nfail, first);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, L);
+  SET_VECTOR_ELT(out, 1, Z);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("Lentries"));
+  SET_STRING_ELT(nm, 1, Rf_mkChar("Zentries"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(6);
+  return out;
+}
+
+/* ---- device-resident handle: one per vecchia.approx ------------------------------------------ */
+static void handle_finalizer(SEXP ptr) {
+  gpv_handle* h = (gpv_handle*)R_ExternalPtrAddr(ptr);
+  if (h) { gpv_destroy(h); R_ClearExternalPtr(ptr); }
+}
+
+SEXP gpvb200_create(SEXP locsord, SEXP revNNarray, SEXP revCond, SEXP obs) {
+  const int64_t N = Rf_nrows(locsord);
+  const int d = Rf_ncols(locsord), p = Rf_ncols(revNNarray);
+  SEXP nn = PROTECT(Rf_coerceVector(revNNarray, INTSXP));
+  int* ip = INTEGER(nn);
+  for (R_xlen_t i = 0; i < XLENGTH(nn); ++i) if (ip[i] == NA_INTEGER) ip[i] = 0;   /* createU.R:146-147 */
+  SEXP ob = PROTECT(Rf_coerceVector(obs, LGLSXP));
+  gpv_handle* h = NULL;
+  check(gpv_create(&h, N, p, d, REAL(locsord), ip, LOGICAL(revCond), GPV_COND_RLOGICAL_I32,
+                   LOGICAL(ob), 0, N, device_from_option()));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(h, Rf_install("gpv_handle"), R_NilValue));
+  R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  UNPROTECT(3);
+  return ptr;
+}
+
+static gpv_handle* get_handle(SEXP ptr) {
+  gpv_handle* h = (gpv_handle*)R_ExternalPtrAddr(ptr);
+  if (!h) Rf_error("gpvecchia_b200: stale device handle (vecchia.approx was deserialised?); re-create it");
+  return h;
+}
+
+SEXP gpvb200_set_revcond(SEXP ptr, SEXP revCond) {
+  check(gpv_set_revcond(get_handle(ptr), LOGICAL(revCond), GPV_COND_RLOGICAL_I32));
+  return R_NilValue;
+}
+
+/* allLentries of createU.R:158-160 (packed U values followed by Zentries), straight from the GPU */
+SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
+  gpv_handle* h = get_handle(ptr);
+  const int64_t n = XLENGTH(nuggets_ord);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(gpv_packed_len(h) + 2 * n)));
+  int64_t nfail = 0, first = -1;
+  check(gpv_u_values_packed(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                            REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first));
+  warn_fail(nfail, first);
+  UNPROTECT(1);
+  return out;
+}
+
+/* c(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, no U materialisation */
+SEXP gpvb200_loglik_numerator(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord,
+                              SEXP nuggets_ord, SEXP zord, SEXP skip_rows) {
+  gpv_handle* h = get_handle(ptr);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
+  check(gpv_loglik_numerator(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                             REAL(nuggets_all_ord), REAL(nuggets_ord), REAL(zord), XLENGTH(zord),
+                             (int64_t)Rf_asReal(skip_rows), -1, REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+SEXP gpvb200_MaternFun(SEXP distmat, SEXP covparms) {
+  SEXP out = PROTECT(Rf_duplicate(distmat));
+  check(gpv_MaternFun(REAL(distmat), XLENGTH(distmat), REAL(covparms), REAL(out), device_from_option()));
+  UNPROTECT(1);
+  return out;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_GPvecchia_U_NZentries", (DL_FUNC)&gpvb200_U_NZentries, 9},   /* same name and arity as
+                                                                       src/RcppExports.cpp:159 */
+    {"_GPvecchia_b200_create", (DL_FUNC)&gpvb200_create, 4},
+    {"_GPvecchia_b200_set_revcond", (DL_FUNC)&gpvb200_set_revcond, 2},
+    {"_GPvecchia_b200_U_values", (DL_FUNC)&gpvb200_U_values, 5},
+    {"_GPvecchia_b200_loglik_numerator", (DL_FUNC)&gpvb200_loglik_numerator, 7},
+    {"_GPvecchia_b200_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},
+    {NULL, NULL, 0}};
+
+void R_init_GPvecchiaB200(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}

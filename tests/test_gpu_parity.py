@@ -328,3 +328,56 @@ def test_harness_gpu_ordered_nn_matches_host_search(d, m, n):
     assert got.shape == ref.shape and np.array_equal(got, ref)
     a, b = n // 3, min(n, n // 3 + 777)
     assert np.array_equal(H.ordered_nn_gpu(locs, m, a, b), ref[a:b])
+
+
+def test_cfg4_shape_m40_3d_esqe():
+    # BASELINE configs[3] at reduced n: 3-D locations, m = 40 (p = 41 > 32: one set per warp), esqe
+    n, m, d = 3000, 40, 3
+    va = _problem(n, m, d, "z", stream=80)
+    rng_ = H.default_range(n, d)
+    cp = [1.0, rng_, 0.5, rng_]
+    nug = H.make_nuggets(n, stream=80)
+    got, ref = _both(va, "esqe", cp, nug, nug)
+    assert got["nfail"] == 0 and np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+    z = H.make_data(n, stream=80)
+    q, l, _ = G.vecchia_loglik_numerator(z, va, cp, nug, covmodel="esqe")
+    qr, lr, _ = O.loglik_numerator_from_U(z, O.createU(va, cp, nug, covmodel="esqe"))
+    assert abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
+
+
+@pytest.mark.parametrize("m", [33, 40, 45, 50, 63])
+def test_large_set_sizes(m):
+    n = 1200
+    va = _problem(n, m, 2, "z", stream=90 + m)
+    cp = [1.0, H.default_range(n, 2), 0.5]
+    nug = np.full(n, 0.1)
+    got, ref = _both(va, "matern", cp, nug, nug)
+    assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+    assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+
+
+def test_cfg5_obs_pred_joint_ordering_zy():
+    # BASELINE configs[4] at reduced n: obs-then-pred ordering, default cond.yz = 'zy' with
+    # prediction locations (vecchia_specify.R:92-96,191-224): N = 2 n_obs + n_pred rows
+    n_obs, n_pred, m = 700, 180, 30
+    locs = H.make_locs(n_obs, 2, stream=85)
+    locs_pred = H.make_locs(n_pred, 2, stream=86)
+    va = O.vecchia_specify(locs, m, cond_yz="zy", locs_pred=locs_pred)
+    assert va["locsord"].shape[0] == 2 * n_obs + n_pred
+    cp = [1.0, H.default_range(n_obs, 2), 1.5]
+    tau = H.make_nuggets(n_obs, stream=85)
+    Ug, Uo, Uq = G.createU(va, cp, tau), O.createU(va, cp, tau), O.createU(va, cp, tau, mode=2)
+    A, B, Q = Ug["U"].tocsc(), Uo["U"].tocsc(), Uq["U"].tocsc()
+    for M in (A, B, Q):
+        M.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    colmax = np.maximum.reduceat(np.abs(Q.data), Q.indptr[:-1])
+    scale = np.repeat(colmax, np.diff(Q.indptr))
+    err_gpu = (np.abs(A.data - Q.data) / scale).max()
+    err_ref = (np.abs(B.data - Q.data) / scale).max()
+    assert err_gpu < max(VAL_TOL, 3 * err_ref), (err_gpu, err_ref)
+    z = H.make_data(n_obs, stream=85)
+    q, l, _ = G.vecchia_loglik_numerator(z, va, cp, tau)
+    qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
+    assert abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
