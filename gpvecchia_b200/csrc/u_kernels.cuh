@@ -108,7 +108,7 @@ __device__ __forceinline__ double rsqrt_seed(double a) {
   return y;
 }
 // 1/sqrt(a) for finite normal a > 0 to ~1 ulp: cubic step (+ a Newton step).
-// a = +Inf returns +0; a <= 0 / NaN: garbage, callers test `a > 0` themselves.
+// a <= 0 / NaN / Inf: garbage, callers test `a > 0` themselves (nuggets are clamped at 1e300).
 __device__ __forceinline__ double rsqrt_pos(double a) {
   const double y0 = rsqrt_seed(a);
   const double t = a * y0;
@@ -117,10 +117,16 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
   const double t1 = a * y;                                   // once per set: keep the Newton step
   const double e1 = fma(-t1, y, 1.0);
   y = fma(0.5 * e1, y, y);
-  return (a < 1.7976931348623157e308) ? y : 0.0;
+  return y;
 }
+// An infinite nugget (Vecchia-Laplace marks missing data with nuggets = Inf,
+// R/vecchia_laplace_NR.R:108) must decouple that neighbour (x_j = 0) without producing Inf * 0 in
+// the factorisation: 1e300 does the same to 300 digits and keeps the pivot code select-free.
+// NaN (Inf * 0 from a latent-conditioned Inf nugget, U_NZentries.cpp:47) passes through and fails
+// the row like dpotrf does.
+__device__ __forceinline__ double clamp_nugget(double v) { return (v > 1.0e300) ? 1.0e300 : v; }
 // 1/a for finite normal a > 0 to ~1 ulp (cubic step from the MUFU.RCP64H seed, + optional Newton
-// step); a = +Inf returns +0; a <= 0 / NaN: garbage, callers test `a > 0` themselves.
+// step); a <= 0 / NaN / Inf: garbage, callers test `a > 0` themselves.
 __device__ __forceinline__ double rcp_pos(double a) {
   double y0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
@@ -130,7 +136,7 @@ __device__ __forceinline__ double rcp_pos(double a) {
   const double e1 = fma(-a, y, 1.0);
   y = fma(y, e1, y);
 #endif
-  return (a < 1.7976931348623157e308) ? y : 0.0;
+  return y;
 }
 // sqrt(w) for w >= 0 to ~1 ulp: cubic rsqrt + one Goldschmidt correction.  The 1e-300 guard keeps
 // w == 0 (duplicate locations) away from rsqrt(0) = Inf without a select: sqrt(1e-300) = 1e-150
@@ -221,7 +227,9 @@ struct SetLayout {
   static constexpr int DD = (D > 0) ? D : GPV_MAX_D;
   static constexpr int NLOW = (P + 1) / 2;                 // rows 0..NLOW-1, row q on lane q
   static constexpr int NHIGH = P / 2;                      // rows P-1..NLOW, row P-1-q on lane q
-  static constexpr int kBuf = ((tri_col(P, P) + 1) / 2) * 2;
+  static constexpr int kScratch = tri_col(P, P);           // dump slot for inactive pair stores
+  static constexpr int kBuf = ((tri_col(P, P) + 2) / 2) * 2;
+  static constexpr int kT = P / 2;                         // pair-stage iterations
   static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
   static constexpr int kX = DD * PX;
   static constexpr int kI = PX / 2;                        // P int32 ids
@@ -237,10 +245,16 @@ struct SetLayout {
   static_assert(P >= 2 && P <= 64 && G <= 32, "unsupported set size");
 };
 
+// squared distance between my point (registers) and staged point j.  D == 2 stages the coordinates
+// as double2 (one 16-byte load per partner); other D use one array per coordinate.
 template <int D>
 __device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX, const double* xi, int j, int d) {
   double r2 = 0.0;
-  if (D > 0) {
+  if (D == 2) {
+    const double2 v = reinterpret_cast<const double2*>(xs)[j];
+    const double dx = xi[0] - v.x, dy = xi[1] - v.y;
+    r2 = fma(dy, dy, dx * dx);
+  } else if (D > 0) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       const double dd = xi[c] - xs[c * PX + j];
@@ -262,49 +276,73 @@ __device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX,
 // low point q and its high point P-1-q through the same iteration (independent chains for ILP).
 // Entries that involve padding are computed on dummy coordinates here and zeroed afterwards
 // (zero_pad_columns): only the first m rows of a data set have padding.
-template <int KIND, int G, int P, int D>
-__device__ __forceinline__ void pair_eval_store(const UParams& q, double* __restrict__ As,
-                                                const double* __restrict__ xs, const double* xl,
-                                                const double* xh, int il, int ih, bool lowv,
-                                                bool highv, int t, int d) {
+// Where pair (i, i+t mod P) goes in the packed staged triangle depends only on (i, t): a per-block
+// table (built once per launch) holds, for iteration t and lane q, the two store offsets of the
+// lane's low and high point as 16-bit halves; inactive combinations point at the dump slot.
+template <int G, int P, int D>
+__device__ __forceinline__ void build_store_table(unsigned* __restrict__ stab) {
   using LY = SetLayout<G, P, D>;
-  int jl = il + t; if (jl >= P) jl -= P;
-  int jh = ih + t; if (jh >= P) jh -= P;
-  const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
-  const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
-  const double vl = cov_eval<KIND>(r2l, q);
-  const double vh = cov_eval<KIND>(r2h, q);
-  const bool full = (2 * t < P);                         // even P: t = P/2 is covered by i < P/2 only
-  if (lowv && (full || il < P / 2)) {
-    const int a = il > jl ? il : jl, b = il > jl ? jl : il;
-    As[tri_col(b, P) + a - b] = vl;
-  }
-  if (highv && (full || ih < P / 2)) {
-    const int a = ih > jh ? ih : jh, b = ih > jh ? jh : ih;
-    As[tri_col(b, P) + a - b] = vh;
+  for (int idx = threadIdx.x; idx < LY::kT * G; idx += blockDim.x) {
+    const int t = idx / G + 1, q = idx % G;
+    const bool full = (2 * t < P);                       // even P: t = P/2 is covered by i < P/2 only
+    unsigned lo16 = LY::kScratch, hi16 = LY::kScratch;
+    if (q < LY::NLOW && (full || q < P / 2)) {
+      const int i = q;
+      int j = i + t; if (j >= P) j -= P;
+      const int a = i > j ? i : j, b = i > j ? j : i;
+      lo16 = tri_col(b, P) + a - b;
+    }
+    if (q < LY::NHIGH && (full || (P - 1 - q) < P / 2)) {
+      const int i = P - 1 - q;
+      int j = i + t; if (j >= P) j -= P;
+      const int a = i > j ? i : j, b = i > j ? j : i;
+      hi16 = tri_col(b, P) + a - b;
+    }
+    stab[idx] = lo16 | (hi16 << 16);
   }
 }
 
 template <int KIND, int G, int P, int D>
+__device__ __forceinline__ void pair_eval_store(const UParams& q, double* __restrict__ As,
+                                                const double* __restrict__ xs, const double* xl,
+                                                const double* xh, int il, int ih,
+                                                const unsigned* __restrict__ stab_lane, int t, int d) {
+  using LY = SetLayout<G, P, D>;
+  int jl = il + t; if (jl >= P) jl -= P;
+  int jh = ih + t; if (jh >= P) jh -= P;
+  const unsigned offs = stab_lane[(t - 1) * G];
+  const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
+  const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
+  const double vl = cov_eval<KIND>(r2l, q);
+  const double vh = cov_eval<KIND>(r2h, q);
+  As[offs & 0xffffu] = vl;
+  As[offs >> 16] = vh;
+}
+
+// pair stage: point i evaluates the covariances (i, i+t mod P), t = 1..P/2; every lane carries its
+// low point q and its high point P-1-q through the same iteration (independent chains for ILP).
+// Entries that involve padding are computed on dummy coordinates here and zeroed afterwards:
+// only the first m rows of a data set have padding.
+template <int KIND, int G, int P, int D>
 __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict__ As,
                                            const double* __restrict__ xs, const double* xl,
-                                           const double* xh, int gl, int d) {
+                                           const double* xh, int gl, const unsigned* __restrict__ stab,
+                                           int d) {
   using LY = SetLayout<G, P, D>;
-  const bool lowv = gl < LY::NLOW;
-  const bool highv = gl < LY::NHIGH;
-  const int il = lowv ? gl : 0;
-  const int ih = highv ? (P - 1 - gl) : (P - 1);
-  constexpr int T = P / 2;
+  const int il = (gl < LY::NLOW) ? gl : 0;
+  const int ih = (gl < LY::NHIGH) ? (P - 1 - gl) : (P - 1);
+  const unsigned* stab_lane = stab + gl;
+  constexpr int T = LY::kT;
   int t = 1;
 #if GPV_PAIR_UNROLL == 2
 #pragma unroll 1
   for (; t + 1 <= T; t += 2) {
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t, d);
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t + 1, d);
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t, d);
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t + 1, d);
   }
 #endif
 #pragma unroll 1
-  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, lowv, highv, t, d);
+  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t, d);
 }
 
 // resident blocks per SM the register allocation is sized for (shared memory allows the same)
@@ -332,6 +370,10 @@ u_sets_kernel(const UParams q) {
   double* buf = smem + (size_t)(warp * SETS + sub) * LY::kDoubles;   // staging, then L
   double* xs = buf + LY::kBuf;
   int* ids = reinterpret_cast<int*>(xs + LY::kX);
+
+  __shared__ unsigned stab[(LY::kT > 0 ? LY::kT : 1) * G];
+  build_store_table<G, P, D>(stab);
+  __syncthreads();
 
   const bool lowv = gl < NLOW;
   const bool highv = gl < NHIGH;
@@ -388,7 +430,7 @@ u_sets_kernel(const UParams q) {
       }
       // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
       cl = (cmask >> ((rl - (P - p)) & 63)) & 1ull;
-      dgl = q.c0 + q.nuggets[idl] * (1.0 - (cl ? 1.0 : 0.0));   // Inf * 0 = NaN kept on purpose
+      dgl = q.c0 + clamp_nugget(q.nuggets[idl] * (1.0 - (cl ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
     }
     if (idh >= 0) {
       if (D == 2) {
@@ -399,22 +441,27 @@ u_sets_kernel(const UParams q) {
         for (int c = 0; c < LY::DD; ++c) if (c < d) xh[c] = q.locs[(int64_t)idh * d + c];
       }
       ch = (cmask >> ((rh - (P - p)) & 63)) & 1ull;
-      dgh = q.c0 + q.nuggets[idh] * (1.0 - (ch ? 1.0 : 0.0));
+      dgh = q.c0 + clamp_nugget(q.nuggets[idh] * (1.0 - (ch ? 1.0 : 0.0)));
     }
+    if (D == 2) {
+      if (lowv) reinterpret_cast<double2*>(xs)[rl] = make_double2(xl[0], xl[1]);
+      if (highv) reinterpret_cast<double2*>(xs)[rh] = make_double2(xh[0], xh[1]);
+    } else {
 #pragma unroll
-    for (int c = 0; c < LY::DD; ++c) {
-      if (lowv) xs[c * PX + rl] = xl[c];
-      if (highv) xs[c * PX + rh] = xh[c];
+      for (int c = 0; c < LY::DD; ++c) {
+        if (lowv) xs[c * PX + rl] = xl[c];
+        if (highv) xs[c * PX + rh] = xh[c];
+      }
     }
     __syncwarp();
 
     // ---- 3. covariance pairs -> shared staging (column-major lower, even stride) -----------------
     switch (q.cov) {
-      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
-      case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
-      case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
-      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
-      default: pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, d); break;
+      case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
+      case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
+      case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
+      case COV_ESQE: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
+      default: pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
     }
     if (__any_sync(FULL, npad > 0)) {
       // padding occupies the leading indices: every pair with a padded point has its smaller index
