@@ -22,10 +22,18 @@
 
 namespace gpv {
 
-constexpr int kTabDeg = 10;
-constexpr int kTabSubBits = 4;              // 16 intervals per octave of w
+#ifndef GPV_TAB_DEG
+#define GPV_TAB_DEG 11
+#endif
+#ifndef GPV_TAB_SUBBITS
+#define GPV_TAB_SUBBITS 3
+#endif
+constexpr int kTabDeg = GPV_TAB_DEG;
+constexpr int kTabSubBits = GPV_TAB_SUBBITS;   // 2^bits intervals per octave of w
 constexpr int kTabSub = 1 << kTabSubBits;
 constexpr int kTabOctaves = 64;             // covered range of w below its maximum
+constexpr int kTabStride = kTabOctaves * kTabSub;   // fixed row stride: coefficient k of interval i
+                                                    // sits at coef[k * kTabStride + i] (immediate offsets)
 constexpr double kTabSSplit = 16.0;          // s >= split: table holds exp(s) * cov
 
 __host__ __device__ inline int hi32_of(double x) {
@@ -207,30 +215,36 @@ __global__ void build_cov_table_kernel(CovTable t, double inv_range, double* coe
     cheb_fit_to_monomial(f, 1.0 / (double)(2 * kTabSub), mono);
     // coefficients are for v in mantissa units: w = 2^e * (mc + v) -> absorb nothing, f is a
     // function of the mantissa within a fixed octave, so no extra scaling is needed.
-    for (int k = 0; k < n; ++k) coef_out[(size_t)k * t.nint + idx] = mono[k];
+    for (int k = 0; k < n; ++k) coef_out[(size_t)k * kTabStride + idx] = mono[k];
   }
 }
 #endif  // GPV_DEFINE_TABLE_BUILDER
 
 __device__ __forceinline__ double cov_general(double r2, const UParams& q) {
-  if (r2 == 0.0) return q.c0;                           // Matern.cpp:76-77
   const CovTable& t = q.tab;
   const int hi = __double2hiint(r2);
   const int idx = (hi >> (20 - kTabSubBits)) - t.idx0;
-  if ((unsigned)idx >= (unsigned)t.nint) {              // outside the table (or NaN/Inf/denormal)
-    return matern_general_direct(sqrt(r2) * q.inv_range, t);
-  }
-  const int lo = __double2loint(r2);
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
-  const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
-  const double v = m - mc;
-  const double* cf = t.coef + idx;
-  double acc = __ldg(cf + (size_t)kTabDeg * t.nint);
+  const bool in_table = (unsigned)idx < (unsigned)t.nint;
+  double acc;
+  if (__all_sync(__activemask(), in_table || r2 == 0.0)) {
+    // common case, warp-uniform: every active lane is inside the table (or at distance 0)
+    const int lo = __double2loint(r2);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
+    const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
+    const double v = m - mc;
+    const double* cf = t.coef + (in_table ? idx : 0);
+    acc = __ldg(cf + kTabDeg * kTabStride);
 #pragma unroll
-  for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + (size_t)k * t.nint));
-  if (r2 >= t.w_split) acc *= exp_neg(sqrt_nonneg(r2) * q.inv_range);
-  return acc;
+    for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
+    if (__any_sync(__activemask(), r2 >= t.w_split)) {        // rare: far pairs of the first rows
+      if (r2 >= t.w_split) acc *= exp_neg(sqrt_nonneg(r2) * q.inv_range);
+    }
+  } else {
+    // some lane is outside the table (or NaN/Inf/denormal): direct Temme / CF2 evaluation
+    acc = matern_general_direct(sqrt(r2) * q.inv_range, t);
+  }
+  return (r2 == 0.0) ? q.c0 : acc;                      // Matern.cpp:76-77
 }
 
 }  // namespace gpv

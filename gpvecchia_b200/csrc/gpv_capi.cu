@@ -59,7 +59,7 @@ extern "C" int64_t gpv_launch_count(void) { return g_launches.load(); }
 // kernel registry
 // ------------------------------------------------------------------------------------------------
 namespace gpv {
-static KernelEntry g_entries[64];
+static KernelEntry g_entries[128];
 static int g_nentries = 0;
 static std::once_flag g_reg_once;
 static void register_all() {
@@ -75,13 +75,13 @@ static void register_all() {
   register_kernels_P51(g_entries, &g_nentries);
   register_kernels_P64(g_entries, &g_nentries);
 }
-const KernelEntry* select_kernel(int p, int d) {
+const KernelEntry* select_kernel(int p, int d, bool general) {
   std::call_once(g_reg_once, register_all);
   const int want_d = (d == 2 || d == 3) ? d : 0;
   const KernelEntry* best = nullptr;
   for (int i = 0; i < g_nentries; ++i) {
     const KernelEntry& e = g_entries[i];
-    if (e.D != want_d || e.P < p) continue;
+    if (e.D != want_d || e.P < p || e.general != general) continue;
     if (!best || e.P < best->P) best = &e;
   }
   return best;
@@ -290,8 +290,10 @@ struct gpv_handle {
   double* d_table = nullptr;          // general-nu coefficient table
   int table_doubles = 0;
   int max_blocks = 0;
-  const KernelEntry* entry = nullptr;
+  const KernelEntry* entry = nullptr;       // closed-form kernel
+  const KernelEntry* entry_gen = nullptr;   // general-nu kernel
   int blocks_per_sm = 0, num_sms = 0;
+  int max_blocks_gen = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   bool ev_valid = false;
@@ -354,8 +356,9 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   if (row_begin < 0 || row_end > Nlocs || row_begin > row_end)
     return fail(GPV_ERR_ARG, "gpv_create: bad row range [%lld,%lld)", (long long)row_begin, (long long)row_end);
   if (Nlocs > (int64_t)INT32_MAX) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: Nlocs exceeds int32 ids");
-  const KernelEntry* entry = select_kernel(p, d);
-  if (!entry) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: no kernel instantiated for p=%d (m=%d), d=%d", p, p - 1, d);
+  const KernelEntry* entry = select_kernel(p, d, false);
+  const KernelEntry* entry_gen = select_kernel(p, d, true);
+  if (!entry || !entry_gen) return fail(GPV_ERR_UNSUPPORTED, "gpv_create: no kernel instantiated for p=%d (m=%d), d=%d", p, p - 1, d);
 
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -367,6 +370,7 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   h->device = device; h->Nlocs = Nlocs; h->p = p; h->d = d;
   h->row_begin = row_begin; h->row_end = row_end; h->nrows = row_end - row_begin;
   h->entry = entry;
+  h->entry_gen = entry_gen;
 #define H_TRY(expr)                                                                                 \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
@@ -390,6 +394,16 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
                                                       kThreadsPerBlock, entry->smem_bytes));
   if (h->blocks_per_sm < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry->name); }
   h->max_blocks = h->num_sms * h->blocks_per_sm;
+  {
+    int bps = 0;
+    H_TRY(cudaFuncSetAttribute((const void*)entry_gen->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               entry_gen->smem_bytes));
+    H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)entry_gen->kernel,
+                                                        kThreadsPerBlock, entry_gen->smem_bytes));
+    if (bps < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry_gen->name); }
+    h->max_blocks_gen = h->num_sms * bps;
+    if (h->max_blocks_gen > h->max_blocks) h->max_blocks = h->max_blocks_gen;   // sizes d_partials
+  }
 
   const size_t nr = (size_t)(h->nrows > 0 ? h->nrows : 1);
   H_TRY(cudaMalloc(&h->d_locs, sizeof(double) * (size_t)Nlocs * d));
@@ -578,7 +592,7 @@ static gpv_status setup_cov(const char* covType, const double* covparms, int nco
 static gpv_status ensure_table(gpv_handle* h, CovSetup* cs, cudaStream_t st) {
   if (!cs->needs_table) return GPV_OK;
   CovTable& t = cs->q.tab;
-  const int need = (kTabDeg + 1) * t.nint;
+  const int need = (kTabDeg + 1) * kTabStride;
   if (need > h->table_doubles) {
     if (h->d_table) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(h->d_table); h->d_table = nullptr; }
     CUDA_TRY(cudaMalloc(&h->d_table, sizeof(double) * (size_t)need));
@@ -604,10 +618,12 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
   q.partials = want_loglik ? h->d_partials : nullptr;
   q.nfail = h->d_nfail; q.first_fail = h->d_first_fail;
-  const KernelEntry* e = h->entry;
+  const bool general = (q.cov == COV_GENERAL);
+  const KernelEntry* e = general ? h->entry_gen : h->entry;
+  const int cap = general ? h->max_blocks_gen : h->num_sms * h->blocks_per_sm;
   const int sets_per_block = kWarpsPerBlock * (32 / e->G);
   int64_t want = (h->nrows + sets_per_block - 1) / sets_per_block;
-  int blocks = (int)(want < (int64_t)h->max_blocks ? want : (int64_t)h->max_blocks);
+  int blocks = (int)(want < (int64_t)cap ? want : (int64_t)cap);
   if (blocks < 1) blocks = 1;
   reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
   g_launches++;
@@ -812,7 +828,7 @@ static gpv_status cov_fun_common(const char* covType, const double* dist, int64_
   cudaError_t e = cudaMalloc(&d_in, sizeof(double) * (size_t)len);
   if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * (size_t)len);
   if (e == cudaSuccess && cs.needs_table) {
-    e = cudaMalloc(&d_tab, sizeof(double) * (size_t)(kTabDeg + 1) * cs.q.tab.nint);
+    e = cudaMalloc(&d_tab, sizeof(double) * (size_t)(kTabDeg + 1) * kTabStride);
     if (e == cudaSuccess) {
       cs.q.tab.coef = d_tab;
       build_cov_table_kernel<<<cs.q.tab.nint, 32>>>(cs.q.tab, cs.q.inv_range, d_tab);

@@ -9,13 +9,14 @@ namespace gpv {
 // One entry per compiled instantiation of u_sets_kernel<G,P,D>.
 struct KernelEntry {
   int G, P, D;                                 // D = 0: runtime d <= GPV_MAX_D
+  bool general;                                // general-nu table kernel vs closed forms
   const char* name;
   void (*kernel)(const UParams);
   int smem_bytes;
 };
 
 // Picks the smallest instantiated P >= p for dimension d; nullptr if none.
-const KernelEntry* select_kernel(int p, int d);
+const KernelEntry* select_kernel(int p, int d, bool general);
 
 // Registration helpers implemented in u_inst_*.cu (one file per P so make -j parallelises nvcc).
 void register_kernels_P4(KernelEntry* out, int* n);
