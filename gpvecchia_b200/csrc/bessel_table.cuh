@@ -220,7 +220,7 @@ __global__ void build_cov_table_kernel(CovTable t, double inv_range, double* coe
 }
 #endif  // GPV_DEFINE_TABLE_BUILDER
 
-__device__ __forceinline__ double cov_general(double r2, const UParams& q) {
+__device__ __forceinline__ double cov_general(double r2, const UParams& q, const double* __restrict__ etab) {
   const CovTable& t = q.tab;
   const int hi = __double2hiint(r2);
   const int idx = (hi >> (20 - kTabSubBits)) - t.idx0;
@@ -238,7 +238,7 @@ __device__ __forceinline__ double cov_general(double r2, const UParams& q) {
 #pragma unroll
     for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
     if (__any_sync(__activemask(), r2 >= t.w_split)) {        // rare: far pairs of the first rows
-      if (r2 >= t.w_split) acc *= exp_neg(sqrt_nonneg(r2) * q.inv_range);
+      if (r2 >= t.w_split) acc *= exp_neg(sqrt_pos(r2) * q.inv_range, etab);
     }
   } else {
     // some lane is outside the table (or NaN/Inf/denormal): direct Temme / CF2 evaluation

@@ -221,6 +221,9 @@ __global__ void reset_scalars_kernel(unsigned long long* nfail, long long* first
 }
 __global__ void cov_eval_kernel(const double* __restrict__ dist, int64_t len, UParams q,
                                 double* __restrict__ out) {
+  __shared__ double etab[64];
+  if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= len) return;
   const double dd = dist[i];
@@ -233,8 +236,8 @@ __global__ void cov_eval_kernel(const double* __restrict__ dist, int64_t len, UP
       case COV_EXP: v = q.c0 * exp(-dd * q.c1); break;
       case COV_M15: { double t = dd * q.c1; v = q.c0 * (1.0 + t) * exp(-t); } break;
       case COV_M25: { double t = dd * q.c1; v = q.c0 * exp(-t) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0); } break;
-      case COV_ESQE: v = cov_eval<COV_ESQE>(r2, q); break;
-      default: v = cov_eval<COV_GENERAL>(r2, q); break;
+      case COV_ESQE: v = cov_eval<COV_ESQE>(r2, q, etab); break;
+      default: v = cov_eval<COV_GENERAL>(r2, q, etab); break;
     }
   }
   out[i] = v;
@@ -613,6 +616,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
                               cudaStream_t st, int* nblocks_out) {
   UParams& q = cs->q;
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
+  q.nsets = h->nrows; q.rowmap = nullptr;
   q.locs = h->d_locs; q.nn = h->d_nn; q.cond = h->d_cond; q.nuggets = d_nuggets;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
   q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
@@ -623,7 +627,12 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   const int cap = general ? h->max_blocks_gen : h->num_sms * h->blocks_per_sm;
   const int sets_per_block = kWarpsPerBlock * (32 / e->G);
   int64_t want = (h->nrows + sets_per_block - 1) / sets_per_block;
-  int blocks = (int)(want < (int64_t)cap ? want : (int64_t)cap);
+  int cap_eff = cap;
+  if (const char* env = std::getenv("GPV_BLOCKS_PER_SM")) {      // development knob: occupancy experiments
+    const int b = std::atoi(env);
+    if (b > 0 && b * h->num_sms < cap_eff) cap_eff = b * h->num_sms;
+  }
+  int blocks = (int)(want < (int64_t)cap_eff ? want : (int64_t)cap_eff);
   if (blocks < 1) blocks = 1;
   reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
   g_launches++;

@@ -26,6 +26,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include "exp_coeffs.h"
 
 #ifndef GPV_MAX_D
@@ -50,12 +51,14 @@ struct CovTable {
 
 struct UParams {
   int64_t nrows;          // rows of this shard
+  int64_t nsets;          // conditioning sets handed to the set kernel (<= nrows)
+  const int32_t* rowmap;  // [nsets] shard-local row of each set, or nullptr (set s is row s)
   int64_t row0;           // global index of the first row of the shard
   int p;                  // actual set size m+1 (<= P)
   int d;                  // spatial dimension
   const double* locs;     // [Nlocs][d] row-major
-  const int32_t* nn;      // [nrows][p] row-major, 0-based ids, -1 = missing
-  const uint64_t* cond;   // [nrows] bit j = (revCond[row, j] == TRUE)
+  const int32_t* nn;      // [nsets][p] row-major, 0-based ids, -1 = missing
+  const uint64_t* cond;   // [nsets] bit j = (revCond[row, j] == TRUE)
   const double* nuggets;  // [Nlocs]
   double* out;            // U values or nullptr
   const int64_t* row_off; // packed offsets [nrows] or nullptr (-> row*p, zero filled)
@@ -81,13 +84,22 @@ constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
 // Polynomial / reduction constants live in constant memory so DFMA takes them as c[bank][offset]
 // operands; as literals ptxas re-materialised them with two UMOVs each inside the pair loop
 // (8% of all issued instructions in the first profile, profiles/r01_*).
-__constant__ double kMathC[16] = {
-    GPV_EXP_C0, GPV_EXP_C1, GPV_EXP_C2, GPV_EXP_C3, GPV_EXP_C4, GPV_EXP_C5, GPV_EXP_C6, GPV_EXP_C7,
-    GPV_EXP_C8, GPV_EXP_C9, GPV_EXP_C10, GPV_EXP_C11,
-    1.4426950408889634,            // [12] log2(e)
-    -6.93147180369123816490e-01,   // [13] -ln2 hi
-    -1.90821492927058770002e-10,   // [14] -ln2 lo
-    1.0e-300};                     // [15] sqrt guard
+#ifndef GPV_EXP_TABLE
+#define GPV_EXP_TABLE 1
+#endif
+__constant__ double kMathC[24] = {
+    GPV_EXP_Q0, GPV_EXP_Q1, GPV_EXP_Q2, GPV_EXP_Q3,
+    GPV_EXP_64_OVER_LN2,           // [4]
+    -GPV_EXP_LN2_64_HI,            // [5]
+    -GPV_EXP_LN2_64_LO,            // [6]
+    1.0e-300,                      // [7] sqrt guard
+    GPV_EXP_C2, GPV_EXP_C3, GPV_EXP_C4, GPV_EXP_C5, GPV_EXP_C6, GPV_EXP_C7, GPV_EXP_C8, GPV_EXP_C9,
+    GPV_EXP_C10, GPV_EXP_C11,      // [8..17] no-table polynomial
+    1.4426950408889634,            // [18] log2(e)
+    -6.93147180369123816490e-01,   // [19] -ln2 hi
+    -1.90821492927058770002e-10,   // [20] -ln2 lo
+    0.0, 0.0, 0.0};
+__constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to shared memory per block
 
 #ifndef GPV_MINB32
 #define GPV_MINB32 4
@@ -138,12 +150,12 @@ __device__ __forceinline__ double rcp_pos(double a) {
 #endif
   return y;
 }
-// sqrt(w) for w >= 0 to ~1 ulp: cubic rsqrt + one Goldschmidt correction.  The 1e-300 guard keeps
-// w == 0 (duplicate locations) away from rsqrt(0) = Inf without a select: sqrt(1e-300) = 1e-150
-// rounds away in every use (exp(-1e-150 c) == 1, 1 + 1e-150 c == 1), so r2 == 0 still returns
-// exactly c0 like the reference's `dist == 0` branches; NaN propagates.
-__device__ __forceinline__ double sqrt_nonneg(double w) {
-  w += kMathC[15];
+// sqrt(w) for w > 0 to ~1 ulp: cubic rsqrt + one Goldschmidt correction, no select.  Callers add
+// kSqrtGuard = 1e-300 to the squared distance (fused into its last FMA), which keeps w == 0
+// (duplicate locations) away from rsqrt(0) = Inf: sqrt(1e-300) = 1e-150 rounds away in every use
+// (exp(-1e-150 c) == 1, 1 + 1e-150 c == 1), so a zero distance still returns exactly c0 like the
+// reference's `dist == 0` branches; NaN propagates.
+__device__ __forceinline__ double sqrt_pos(double w) {
   const double y0 = rsqrt_seed(w);
   const double t = w * y0;
   const double e = fma(-t, y0, 1.0);
@@ -153,40 +165,39 @@ __device__ __forceinline__ double sqrt_nonneg(double w) {
   const double r = fma(-g, h, 0.5);
   return fma(g, r, g);
 }
-// exp(-s) for s >= 0 (clamped at s = 700: below 1e-304 either way), ~1 ulp, no branches.
-__device__ __forceinline__ double exp_neg(double s) {
+// exp(-s) for s >= 0 (clamped at s = 700: below 1e-304 either way), ~1 ulp, no branches:
+// -s = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(-s) = 2^k * etab[j] * (1 + p(r)), p of degree 5.
+// etab = 2^(j/64) in shared memory (a 64-entry gather; constant memory would serialise it).
+__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ etab) {
   s = (s > 700.0) ? 700.0 : s;                               // NaN stays NaN
   const double kShift = 6755399441055744.0;                  // 1.5 * 2^52
-  const double t = fma(-s, kMathC[12], kShift);              // round(-s / ln2) in the low mantissa bits
-  const double kf = t - kShift;
-  double r = fma(kf, kMathC[13], -s);
-  r = fma(kf, kMathC[14], r);
-#if GPV_EXP_ESTRIN
-  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-  const double a0 = 1.0 + r;
-  const double a1 = fma(kMathC[3], r, kMathC[2]);
-  const double a2 = fma(kMathC[5], r, kMathC[4]);
-  const double a3 = fma(kMathC[7], r, kMathC[6]);
-  const double a4 = fma(kMathC[9], r, kMathC[8]);
-  const double a5 = fma(kMathC[11], r, kMathC[10]);
-  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
-  const double p = fma(b2, r8, fma(b1, r4, b0));
-#else
-  double p = kMathC[11];
-  p = fma(p, r, kMathC[10]);
-  p = fma(p, r, kMathC[9]);
-  p = fma(p, r, kMathC[8]);
-  p = fma(p, r, kMathC[7]);
-  p = fma(p, r, kMathC[6]);
-  p = fma(p, r, kMathC[5]);
-  p = fma(p, r, kMathC[4]);
-  p = fma(p, r, kMathC[3]);
-  p = fma(p, r, kMathC[2]);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+#if !GPV_EXP_TABLE
+  {
+    const double t = fma(-s, kMathC[18], kShift);            // round(-s / ln2)
+    const double kf = t - kShift;
+    double r = fma(kf, kMathC[19], -s);
+    r = fma(kf, kMathC[20], r);
+    double p = kMathC[17];
+#pragma unroll
+    for (int i = 16; i >= 8; --i) p = fma(p, r, kMathC[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + __double2loint(t) * 1048576, __double2loint(p));
+  }
 #endif
-  const int k = __double2loint(t);                           // -1011 <= k <= 0
-  return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
+  const double t = fma(-s, kMathC[4], kShift);               // round(-64 s / ln2) in the low mantissa bits
+  const double kf = t - kShift;
+  double r = fma(kf, kMathC[5], -s);
+  r = fma(kf, kMathC[6], r);
+  const int n = __double2loint(t);                           // 64 k + j, k <= 0
+  const double T = etab[n & 63];
+  const double r2 = r * r;
+  double qq = fma(kMathC[3], r, kMathC[2]);
+  qq = fma(qq, r, kMathC[1]);
+  qq = fma(qq, r, kMathC[0]);
+  const double p = fma(qq, r2, r);
+  const double v = fma(T, p, T);
+  return __hiloint2double(__double2hiint(v) + (n >> 6) * 1048576, __double2loint(v));
 }
 
 // --------------------------------------------------------------------------------------------
@@ -194,28 +205,25 @@ __device__ __forceinline__ double exp_neg(double s) {
 // every closed form returns exactly c0 at r2 == 0, as the reference's `dist == 0` branches do)
 // --------------------------------------------------------------------------------------------
 __device__ double matern_general_direct(double s, const CovTable& t);  // bessel_table.cuh
-__device__ __forceinline__ double cov_general(double r2, const UParams& q);
+__device__ __forceinline__ double cov_general(double r2, const UParams& q, const double* __restrict__ etab);
 
 template <int KIND>
-__device__ __forceinline__ double cov_eval(double r2, const UParams& q) {
+__device__ __forceinline__ double cov_eval(double r2, const UParams& q, const double* __restrict__ etab) {
   if (KIND == COV_EXP) {          // Matern.cpp:38-39   sig2 exp(-d/range)               c1 = 1/range
-    return q.c0 * exp_neg(sqrt_nonneg(r2) * q.c1);
+    return q.c0 * exp_neg(sqrt_pos(r2) * q.c1, etab);
   } else if (KIND == COV_M15) {   // :51-52  sig2 (1+sqrt3 s) exp(-sqrt3 s)              c1 = sqrt3/range
-    const double t = sqrt_nonneg(r2) * q.c1;
-    return fma(q.c0, t, q.c0) * exp_neg(t);
+    const double t = sqrt_pos(r2) * q.c1;
+    return fma(q.c0, t, q.c0) * exp_neg(t, etab);
   } else if (KIND == COV_M25) {   // :66-68  sig2 exp(-t)(1 + t + t^2/3), t = sqrt5 s     c1 = sqrt5/range
-    const double t = sqrt_nonneg(r2) * q.c1;
-    return q.c0 * exp_neg(t) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0);
+    const double t = sqrt_pos(r2) * q.c1;
+    return q.c0 * exp_neg(t, etab) * fma(t, fma(t, 1.0 / 3.0, 1.0), 1.0);
   } else if (KIND == COV_ESQE) {  // Esqe.cpp:32-34  c4 = sig2_1, c1 = 1/r1, c2 = sig2_2, c3 = 1/r2^2
-    return fma(q.c2, exp_neg(r2 * q.c3), q.c4 * exp_neg(sqrt_nonneg(r2) * q.c1));
+    return fma(q.c2, exp_neg(r2 * q.c3, etab), q.c4 * exp_neg(sqrt_pos(r2) * q.c1, etab));
   } else {
-    return cov_general(r2, q);
+    return cov_general(r2, q, etab);
   }
 }
 
-// --------------------------------------------------------------------------------------------
-// per-set shared-memory layout
-// --------------------------------------------------------------------------------------------
 // Packed lower triangle, column-major: column k holds rows k..P-1 at tri_col(k) + (r - k).  Used both
 // for the staged covariance matrix and, column by column, for L (a column of L overwrites the
 // staged column it was computed from, which is dead by then).  496 doubles for P = 31 instead of
@@ -231,12 +239,20 @@ struct SetLayout {
   static constexpr int kBuf = ((tri_col(P, P) + 2) / 2) * 2;
   static constexpr int kT = P / 2;                         // pair-stage iterations
   static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
-  static constexpr int kX = DD * PX;
-  static constexpr int kI = PX / 2;                        // P int32 ids
+  static constexpr int kX = DD * PX;                       // coordinates of the P points
+  static constexpr int kNug = PX;                          // nuggets of the P points
+  static constexpr int kI = ((PX / 2 + 1) / 2) * 2;        // P int32 compacted ids (kept even)
+  static constexpr int kRawI = G;                          // 2G int32 raw ids of a row (as stored)
+  static constexpr int kMeta = 2;                          // cond mask (8 B), row (4 B), pad
+  // one input stage = everything the pair stage and the epilogue read about a set; two of them so
+  // that cp.async fills stage b^1 while stage b is being factored
+  static constexpr int kStage = kX + kNug + kI + kRawI + kMeta;
+  static constexpr int kOffNug = kX, kOffIds = kX + kNug, kOffRaw = kX + kNug + kI,
+                       kOffMeta = kX + kNug + kI + kRawI;
   static constexpr int kSetsPerWarp = 32 / G;
   // offset consecutive sets of a warp by 128/kSetsPerWarp bytes (mod 128) so that the per-set
   // broadcast loads of one warp instruction fall into different banks
-  static constexpr int kRaw = kBuf + kX + kI;
+  static constexpr int kRaw = kBuf + 2 * kStage;
   static constexpr int kWant = (kSetsPerWarp > 1) ? 16 / kSetsPerWarp : 0;   // doubles, mod 16
   static constexpr int kPad = (kSetsPerWarp > 1) ? ((kWant - (kRaw % 16)) + 16) % 16 : (kRaw % 2);
   static constexpr int kDoubles = kRaw + kPad;
@@ -245,15 +261,17 @@ struct SetLayout {
   static_assert(P >= 2 && P <= 64 && G <= 32, "unsupported set size");
 };
 
-// squared distance between my point (registers) and staged point j.  D == 2 stages the coordinates
-// as double2 (one 16-byte load per partner); other D use one array per coordinate.
+// squared distance between my point (registers) and staged point j, plus `guard` (1e-300 for the
+// closed forms, see sqrt_pos; 0 for the general branch, which tests r2 == 0 itself).  D == 2 stages
+// the coordinates as double2 (one 16-byte load per partner); other D use one array per coordinate.
 template <int D>
-__device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX, const double* xi, int j, int d) {
-  double r2 = 0.0;
+__device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX, const double* xi, int j,
+                                          int d, double guard) {
+  double r2 = guard;
   if (D == 2) {
     const double2 v = reinterpret_cast<const double2*>(xs)[j];
     const double dx = xi[0] - v.x, dy = xi[1] - v.y;
-    r2 = fma(dy, dy, dx * dx);
+    r2 = fma(dy, dy, fma(dx, dx, guard));
   } else if (D > 0) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -272,10 +290,6 @@ __device__ __forceinline__ double pair_r2(const double* __restrict__ xs, int PX,
   return r2;
 }
 
-// pair stage: point i evaluates the covariances (i, i+t mod P), t = 1..P/2; every lane carries its
-// low point q and its high point P-1-q through the same iteration (independent chains for ILP).
-// Entries that involve padding are computed on dummy coordinates here and zeroed afterwards
-// (zero_pad_columns): only the first m rows of a data set have padding.
 // Where pair (i, i+t mod P) goes in the packed staged triangle depends only on (i, t): a per-block
 // table (built once per launch) holds, for iteration t and lane q, the two store offsets of the
 // lane's low and high point as 16-bit halves; inactive combinations point at the dump slot.
@@ -306,15 +320,17 @@ template <int KIND, int G, int P, int D>
 __device__ __forceinline__ void pair_eval_store(const UParams& q, double* __restrict__ As,
                                                 const double* __restrict__ xs, const double* xl,
                                                 const double* xh, int il, int ih,
-                                                const unsigned* __restrict__ stab_lane, int t, int d) {
+                                                const unsigned* __restrict__ stab_lane,
+                                                const double* __restrict__ etab, int t, int d) {
   using LY = SetLayout<G, P, D>;
   int jl = il + t; if (jl >= P) jl -= P;
   int jh = ih + t; if (jh >= P) jh -= P;
   const unsigned offs = stab_lane[(t - 1) * G];
-  const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d);
-  const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d);
-  const double vl = cov_eval<KIND>(r2l, q);
-  const double vh = cov_eval<KIND>(r2h, q);
+  const double guard = (KIND == COV_GENERAL) ? 0.0 : kMathC[7];
+  const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d, guard);
+  const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d, guard);
+  const double vl = cov_eval<KIND>(r2l, q, etab);
+  const double vh = cov_eval<KIND>(r2h, q, etab);
   As[offs & 0xffffu] = vl;
   As[offs >> 16] = vh;
 }
@@ -327,7 +343,7 @@ template <int KIND, int G, int P, int D>
 __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict__ As,
                                            const double* __restrict__ xs, const double* xl,
                                            const double* xh, int gl, const unsigned* __restrict__ stab,
-                                           int d) {
+                                           const double* __restrict__ etab, int d) {
   using LY = SetLayout<G, P, D>;
   const int il = (gl < LY::NLOW) ? gl : 0;
   const int ih = (gl < LY::NHIGH) ? (P - 1 - gl) : (P - 1);
@@ -337,12 +353,12 @@ __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict_
 #if GPV_PAIR_UNROLL == 2
 #pragma unroll 1
   for (; t + 1 <= T; t += 2) {
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t, d);
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t + 1, d);
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t, d);
+    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t + 1, d);
   }
 #endif
 #pragma unroll 1
-  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, t, d);
+  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t, d);
 }
 
 // resident blocks per SM the register allocation is sized for (shared memory allows the same)
@@ -371,12 +387,13 @@ u_sets_kernel(const UParams q) {
   const int d = (D > 0) ? D : q.d;
   const int p = q.p;
 
-  double* buf = smem + (size_t)(warp * SETS + sub) * LY::kDoubles;   // staging, then L
-  double* xs = buf + LY::kBuf;
-  int* ids = reinterpret_cast<int*>(xs + LY::kX);
+  double* buf = smem + (size_t)(warp * SETS + sub) * LY::kDoubles;   // staged triangle, then L
+  double* stage0 = buf + LY::kBuf;                                   // two input stages
 
   __shared__ unsigned stab[(LY::kT > 0 ? LY::kT : 1) * G];
+  __shared__ double etab[64];
   build_store_table<G, P, D>(stab);
+  if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
   __syncthreads();
 
   const bool lowv = gl < NLOW;
@@ -386,88 +403,137 @@ u_sets_kernel(const UParams q) {
 
   double acc_quad = 0.0, acc_logd = 0.0;
   const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock * SETS;
+  const int64_t first = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * SETS;
 
-  for (int64_t r0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * SETS; r0 < q.nrows; r0 += stride) {
-    const int64_t row = r0 + sub;
-    const bool row_ok = row < q.nrows;
-
-    // ---- 1. ids, compaction (U_NZentries.cpp:41-45): entries gl and gl + G of the row ---------
-    int raw0 = -1, raw1 = -1;
-    if (row_ok) {
-      const int32_t* nnr = q.nn + row * (int64_t)p;
-      if (gl < p) raw0 = nnr[gl];
-      if (gl + G < p) raw1 = nnr[gl + G];
+  // ---- input pipeline (cp.async, no registers held across the factorisation) ----------------------
+  // fetch_raw(s, st): the row of neighbour ids, its revCond mask and its row number -> stage st
+  auto fetch_raw = [&](int64_t sidx, double* st) {
+    int* raw = reinterpret_cast<int*>(st + LY::kOffRaw);
+    double* meta = st + LY::kOffMeta;
+    int* metai = reinterpret_cast<int*>(meta + 1);
+    if (sidx < q.nsets) {
+      const int32_t* nnr = q.nn + sidx * (int64_t)p;
+      if (gl < p) __pipeline_memcpy_async(raw + gl, nnr + gl, 4); else raw[gl] = -1;
+      if (gl + G < p) __pipeline_memcpy_async(raw + gl + G, nnr + gl + G, 4); else raw[gl + G] = -1;
+      if (gl == 0) {
+        __pipeline_memcpy_async(meta, q.cond + sidx, 8);
+        if (q.rowmap != nullptr) __pipeline_memcpy_async(metai, q.rowmap + sidx, 4);
+        else metai[0] = (int)sidx;
+      }
+    } else {
+      raw[gl] = -1;
+      raw[gl + G] = -1;
+      if (gl == 0) { reinterpret_cast<unsigned long long*>(meta)[0] = 0ull; metai[0] = -1; }
     }
+  };
+  // gather(st): compaction of the raw ids (U_NZentries.cpp:41-45: entries gl and gl + G of the row),
+  // then coordinates and nuggets of my two points -> stage st.  Returns n0.
+  auto gather = [&](double* st) -> int {
+    const int* raw = reinterpret_cast<const int*>(st + LY::kOffRaw);
+    int* ids = reinterpret_cast<int*>(st + LY::kOffIds);
+    double* xs = st;
+    double* nug = st + LY::kOffNug;
+    const int raw0 = raw[gl], raw1 = raw[gl + G];
     const unsigned b0 = (__ballot_sync(FULL, raw0 >= 0) >> base) & gmask;
     const unsigned b1 = (__ballot_sync(FULL, raw1 >= 0) >> base) & gmask;
-    const unsigned anyvalid = __ballot_sync(FULL, (raw0 >= 0) | (raw1 >= 0));
-    if (anyvalid == 0u) continue;                      // warp-uniform: nothing to factor
     const int n0 = __popc(b0) + __popc(b1);
     const int npad = P - n0;
-    {
-      const unsigned below = (1u << gl) - 1u;
-      if (gl < npad) ids[gl] = -1;
-      if (gl + G < npad) ids[gl + G] = -1;
-      __syncwarp();
-      if (raw0 >= 0) ids[npad + __popc(b0 & below)] = raw0;
-      if (raw1 >= 0) ids[npad + __popc(b0) + __popc(b1 & below)] = raw1;
-      __syncwarp();
+    const unsigned below = (1u << gl) - 1u;
+    if (gl < npad) ids[gl] = -1;
+    if (gl + G < npad) ids[gl + G] = -1;
+    __syncwarp();
+    if (raw0 >= 0) ids[npad + __popc(b0 & below)] = raw0;
+    if (raw1 >= 0) ids[npad + __popc(b0) + __popc(b1 & below)] = raw1;
+    __syncwarp();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const bool valid = which ? highv : lowv;
+      const int r = which ? rh : rl;
+      if (!valid) continue;
+      const int id = ids[r];
+      if (id >= 0) {
+        if (D == 2) {
+          __pipeline_memcpy_async(xs + 2 * r, q.locs + 2 * (int64_t)id, 16);
+        } else {
+          for (int c = 0; c < d; ++c) __pipeline_memcpy_async(xs + c * PX + r, q.locs + (int64_t)id * d + c, 8);
+        }
+        __pipeline_memcpy_async(nug + r, q.nuggets + id, 8);
+      } else {
+        if (D == 2) {
+          reinterpret_cast<double2*>(xs)[r] = make_double2(0.0, 0.0);
+        } else {
+          for (int c = 0; c < d; ++c) xs[c * PX + r] = 0.0;
+        }
+        nug[r] = 0.0;
+      }
     }
-    const uint64_t cmask = row_ok ? q.cond[row] : 0ull;
+    return n0;
+  };
 
-    // ---- 2. gather coordinates and nuggets of my two points -------------------------------------
+  int bsel = 0;
+  fetch_raw(first + sub, stage0);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncwarp();
+  int n0 = gather(stage0);
+  fetch_raw(first + stride + sub, stage0 + LY::kStage);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncwarp();
+
+  for (int64_t s0 = first; s0 < q.nsets; s0 += stride) {
+    double* st = stage0 + bsel * LY::kStage;
+    double* stn = stage0 + (bsel ^ 1) * LY::kStage;
+    // meta of the current set into registers, then its raw/meta slots are free for set i+2
+    const uint64_t cmask = reinterpret_cast<const unsigned long long*>(st + LY::kOffMeta)[0];
+    const int row = reinterpret_cast<const int*>(st + LY::kOffMeta + 1)[0];
+    const bool row_ok = row >= 0;
+    const int npad = P - n0;
+    const int n0_next = gather(stn);                       // set i+1: ids now, coordinates in flight
+    __syncwarp();
+    fetch_raw(s0 + 2 * stride + sub, st);                  // set i+2: ids in flight
+    __pipeline_commit();
+
+    // ---- 1./2. my two points of the current set (staged by the previous iteration) ---------------
+    const double* xs = st;
+    const int* ids = reinterpret_cast<const int*>(st + LY::kOffIds);
+    const double* nugs = st + LY::kOffNug;
     double xl[LY::DD], xh[LY::DD];
     double dgl = 1.0, dgh = 1.0;
     int idl = -1, idh = -1;
     bool cl = false, ch = false;
     if (lowv) idl = ids[rl];
     if (highv) idh = ids[rh];
-#pragma unroll
-    for (int c = 0; c < LY::DD; ++c) { xl[c] = 0.0; xh[c] = 0.0; }
-    if (idl >= 0) {
-      if (D == 2) {
-        const double2 v = reinterpret_cast<const double2*>(q.locs)[idl];
-        xl[0] = v.x; xl[1] = v.y;
-      } else {
-#pragma unroll
-        for (int c = 0; c < LY::DD; ++c) if (c < d) xl[c] = q.locs[(int64_t)idl * d + c];
-      }
-      // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
-      cl = (cmask >> ((rl - (P - p)) & 63)) & 1ull;
-      dgl = q.c0 + clamp_nugget(q.nuggets[idl] * (1.0 - (cl ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
-    }
-    if (idh >= 0) {
-      if (D == 2) {
-        const double2 v = reinterpret_cast<const double2*>(q.locs)[idh];
-        xh[0] = v.x; xh[1] = v.y;
-      } else {
-#pragma unroll
-        for (int c = 0; c < LY::DD; ++c) if (c < d) xh[c] = q.locs[(int64_t)idh * d + c];
-      }
-      ch = (cmask >> ((rh - (P - p)) & 63)) & 1ull;
-      dgh = q.c0 + clamp_nugget(q.nuggets[idh] * (1.0 - (ch ? 1.0 : 0.0)));
-    }
     if (D == 2) {
-      if (lowv) reinterpret_cast<double2*>(xs)[rl] = make_double2(xl[0], xl[1]);
-      if (highv) reinterpret_cast<double2*>(xs)[rh] = make_double2(xh[0], xh[1]);
+      const double2 vl = reinterpret_cast<const double2*>(xs)[rl];
+      const double2 vh = reinterpret_cast<const double2*>(xs)[rh];
+      xl[0] = vl.x; xl[1] = vl.y; xh[0] = vh.x; xh[1] = vh.y;
     } else {
 #pragma unroll
       for (int c = 0; c < LY::DD; ++c) {
-        if (lowv) xs[c * PX + rl] = xl[c];
-        if (highv) xs[c * PX + rh] = xh[c];
+        xl[c] = (c < d) ? xs[c * PX + rl] : 0.0;
+        xh[c] = (c < d) ? xs[c * PX + rh] : 0.0;
       }
     }
-    __syncwarp();
+    if (idl >= 0) {
+      // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
+      cl = (cmask >> ((rl - (P - p)) & 63)) & 1ull;
+      dgl = q.c0 + clamp_nugget(nugs[rl] * (1.0 - (cl ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
+    }
+    if (idh >= 0) {
+      ch = (cmask >> ((rh - (P - p)) & 63)) & 1ull;
+      dgh = q.c0 + clamp_nugget(nugs[rh] * (1.0 - (ch ? 1.0 : 0.0)));
+    }
 
     // ---- 3. covariance pairs -> shared staging (column-major lower, even stride) -----------------
     if (GENERAL) {
-      pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, stab, d);
+      pair_stage<COV_GENERAL, G, P, D>(q, buf, xs, xl, xh, gl, stab, etab, d);
     } else {
       switch (q.cov) {
-        case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
-        case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
-        case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
-        default: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, stab, d); break;
+        case COV_EXP: pair_stage<COV_EXP, G, P, D>(q, buf, xs, xl, xh, gl, stab, etab, d); break;
+        case COV_M15: pair_stage<COV_M15, G, P, D>(q, buf, xs, xl, xh, gl, stab, etab, d); break;
+        case COV_M25: pair_stage<COV_M25, G, P, D>(q, buf, xs, xl, xh, gl, stab, etab, d); break;
+        default: pair_stage<COV_ESQE, G, P, D>(q, buf, xs, xl, xh, gl, stab, etab, d); break;
       }
     }
     if (__any_sync(FULL, npad > 0)) {
@@ -503,7 +569,8 @@ u_sets_kernel(const UParams q) {
     for (int k = 0; k < P; ++k) {
       const double akk = (k < NLOW) ? __shfl_sync(FULL, lo[k < NLOW ? k : 0], base + k)
                                     : __shfl_sync(FULL, hi[k], base + (P - 1 - k));
-      fail = fail || !(akk > 0.0);
+      // positive, normal, finite -- dpotrf's `ajj <= 0 || isnan(ajj)` test on the integer pipe
+      fail = fail || ((unsigned)(__double2hiint(akk) - 0x00100000) >= 0x7fe00000u);
       if (k == P - 1) { dlast = akk; break; }
       const double inv = rcp_pos(akk);      // +Inf -> 0 : an Inf nugget decouples that neighbour
       // publish L[r][k] = a[r][k] / d_k for r >= k (a packed column must not be written above its top)
@@ -568,7 +635,7 @@ u_sets_kernel(const UParams q) {
         if (idl >= 0) o[rl - npad] = xlow;
         if (idh >= 0) o[rh - npad] = xhigh;
       } else {
-        double* o = q.out + row * (int64_t)p;
+        double* o = q.out + (int64_t)row * p;
         if (idl >= 0) o[rl - npad] = xlow;
         if (idh >= 0) o[rh - npad] = xhigh;
         if (gl >= n0 && gl < p) o[gl] = 0.0;             // zero fill beyond n0 (:33)
@@ -594,7 +661,10 @@ u_sets_kernel(const UParams q) {
         acc_logd += log(xself);
       }
     }
+    __pipeline_wait_prior(0);                              // set i+1 staged, ids of set i+2 landed
     __syncwarp();
+    n0 = n0_next;
+    bsel ^= 1;
   }
 
   // ---- deterministic block reduction of the likelihood partial sums ---------------------------------
