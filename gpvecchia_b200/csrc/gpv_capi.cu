@@ -106,6 +106,91 @@ __global__ void prep_nn_kernel(const int32_t* __restrict__ nn_cm, int64_t Nlocs,
   }
   n0_out[r] = n0;
 }
+// rows with n0 >= 2 go to the set kernel; rows with n0 <= 1 (the n dummy rows of a `zy` layout,
+// vecchia_specify.R:205-206, and row 1 of every layout) are closed form: x = 1/sqrt(C(0) + nug)
+__global__ void classify_rows_kernel(const int64_t* __restrict__ n0, int64_t nrows,
+                                     int32_t* __restrict__ is_full, int32_t* __restrict__ is_triv) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  is_full[r] = n0[r] >= 2;
+  is_triv[r] = n0[r] <= 1;
+}
+__global__ void scatter_rows_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos,
+                                    int64_t nrows, int32_t* __restrict__ list) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows && flag[r]) list[pos[r]] = (int32_t)r;
+}
+__global__ void gather_nn_rows_kernel(const int32_t* __restrict__ nn, const int32_t* __restrict__ rowmap,
+                                      int64_t nsets, int p, int32_t* __restrict__ nn_full) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsets * p) return;
+  const int64_t s = i / p;
+  const int j = (int)(i - s * p);
+  nn_full[i] = nn[(int64_t)rowmap[s] * p + j];
+}
+__global__ void gather_cond_rows_kernel(const uint64_t* __restrict__ cond, const int32_t* __restrict__ rowmap,
+                                        int64_t nsets, uint64_t* __restrict__ cond_full) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nsets) cond_full[s] = cond[rowmap[s]];
+}
+// one thread per row with n0 <= 1 (U_NZentries.cpp:39-69 with a 1x1 block; n0 == 0 rows stay zero)
+__global__ void trivial_rows_kernel(UParams q, const int32_t* __restrict__ nn_rows,
+                                    const uint64_t* __restrict__ cond_rows, const int32_t* __restrict__ list,
+                                    int64_t nlist, double* __restrict__ partials) {
+  __shared__ double red[8][2];
+  double acc_quad = 0.0, acc_logd = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nlist;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = list[i];
+    const int32_t* nnr = nn_rows + row * q.p;
+    int id = -1;
+    for (int j = 0; j < q.p; ++j) { const int v = nnr[j]; if (v >= 0) id = v; }
+    double x = 0.0;
+    bool condbit = false;
+    if (id >= 0) {
+      condbit = (cond_rows[row] >> (q.p - 1)) & 1ull;       // revCond[row, p - n0 + 0], n0 = 1 (:47)
+      const double nug = q.nuggets[id] * (1.0 - (condbit ? 1.0 : 0.0));
+      const double a = q.c0 + nug;
+      if (a > 0.0) {                                         // chol of a 1x1 block
+        x = 1.0 / sqrt(a);                                   // a = +Inf -> 0 like the reference
+      } else {                                               // <= 0 or NaN: row stays zero (:64-66)
+        atomicAdd(q.nfail, 1ull);
+        atomicMin(q.first_fail, (long long)(q.row0 + row));
+      }
+    }
+    if (q.out != nullptr) {
+      if (q.row_off != nullptr) {
+        if (id >= 0) q.out[q.row_off[row]] = x;
+      } else {
+        double* o = q.out + row * (int64_t)q.p;
+        o[0] = x;
+        for (int j = 1; j < q.p; ++j) o[j] = 0.0;
+      }
+    }
+    if (partials != nullptr && id >= 0 && (q.row0 + row) >= q.skip_rows) {
+      double t = 0.0;
+      if (!condbit) { const int orank = q.obsrank[id]; if (orank >= 0) t = x * q.zord[orank]; }
+      acc_quad += t * t;
+      acc_logd += log(x);
+    }
+  }
+  if (partials != nullptr) {
+    for (int o = 16; o >= 1; o >>= 1) {
+      acc_quad += __shfl_xor_sync(0xffffffffu, acc_quad, o);
+      acc_logd += __shfl_xor_sync(0xffffffffu, acc_logd, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s0 = 0, s1 = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s0 += red[w][0]; s1 += red[w][1]; }
+      partials[2 * blockIdx.x] = s0;
+      partials[2 * blockIdx.x + 1] = s1;
+    }
+  }
+}
+
 template <typename T>
 __device__ inline bool cond_is_true(T v);
 template <>
@@ -277,6 +362,13 @@ struct gpv_handle {
   uint64_t* d_cond = nullptr;         // [nrows]
   int64_t* d_row_off = nullptr;       // [nrows]
   int32_t* d_obsrank = nullptr;       // [Nlocs]
+  // row split (only when >= 1/64 of the rows have n0 <= 1, e.g. `zy` layouts)
+  bool split = false;
+  int64_t nfull = 0, ntriv = 0;
+  int32_t* d_rowmap = nullptr;        // [nfull] rows with n0 >= 2
+  int32_t* d_nn_full = nullptr;       // [nfull][p]
+  uint64_t* d_cond_full = nullptr;    // [nfull]
+  int32_t* d_trivlist = nullptr;      // [ntriv] rows with n0 <= 1
   // per-call scratch (allocated lazily, reused)
   double* d_nuggets = nullptr;        // [Nlocs]
   double* d_tau = nullptr;            // [n_obs]
@@ -303,12 +395,14 @@ struct gpv_handle {
   const char* last_kernel = "";
 };
 static const int kObsBlocks = 296;
+static const int kTrivBlocks = 296;
 
 static void free_handle(gpv_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
-  cudaFree(h->d_obsrank); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
+  cudaFree(h->d_obsrank); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
+  cudaFree(h->d_trivlist); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
   cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
   cudaFree(h->d_first_fail); cudaFree(h->d_table);
@@ -330,6 +424,11 @@ static gpv_status upload_cond(gpv_handle* h, const void* host) {
     prep_cond_kernel<T><<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, h->Nlocs, h->p,
                                                                         h->row_begin, h->nrows, h->d_cond);
     g_launches++;
+    if (h->split && h->nfull > 0) {
+      gather_cond_rows_kernel<<<grid_for(h->nfull, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap, h->nfull,
+                                                                              h->d_cond_full);
+      g_launches++;
+    }
     e = cudaStreamSynchronize(h->stream);
   }
   cudaFree(tmp);
@@ -414,7 +513,7 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   H_TRY(cudaMalloc(&h->d_cond, sizeof(uint64_t) * nr));
   H_TRY(cudaMalloc(&h->d_row_off, sizeof(int64_t) * nr));
   H_TRY(cudaMalloc(&h->d_nuggets, sizeof(double) * (size_t)Nlocs));
-  H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * (size_t)h->max_blocks));
+  H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * (size_t)(h->max_blocks + kTrivBlocks)));
   H_TRY(cudaMalloc(&h->d_obs_partials, sizeof(double) * 2 * kObsBlocks));
   H_TRY(cudaMalloc(&h->d_loglik, sizeof(double) * 3));
   H_TRY(cudaMalloc(&h->d_nfail, sizeof(unsigned long long)));
@@ -464,6 +563,50 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_off, h->d_row_off + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_n0, n0 + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    // row classes
+    int32_t *is_full = nullptr, *is_triv = nullptr, *pos_full = nullptr, *pos_triv = nullptr;
+    void* scan2 = nullptr;
+    size_t scan2_bytes = 0;
+    int32_t lf = 0, lpf = 0, lt = 0, lpt = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&is_full, sizeof(int32_t) * nr);
+    if (e == cudaSuccess) e = cudaMalloc(&is_triv, sizeof(int32_t) * nr);
+    if (e == cudaSuccess) e = cudaMalloc(&pos_full, sizeof(int32_t) * nr);
+    if (e == cudaSuccess) e = cudaMalloc(&pos_triv, sizeof(int32_t) * nr);
+    if (e == cudaSuccess) {
+      classify_rows_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(n0, h->nrows, is_full, is_triv);
+      g_launches++;
+      e = cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, is_full, pos_full, (int)h->nrows, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&scan2, scan2_bytes ? scan2_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(scan2, scan2_bytes, is_full, pos_full, (int)h->nrows, h->stream);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(scan2, scan2_bytes, is_triv, pos_triv, (int)h->nrows, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lf, is_full + (h->nrows - 1), 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lpf, pos_full + (h->nrows - 1), 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lt, is_triv + (h->nrows - 1), 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lpt, pos_triv + (h->nrows - 1), 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) {
+      h->nfull = (int64_t)lf + lpf;
+      h->ntriv = (int64_t)lt + lpt;
+      h->split = h->ntriv * 64 >= h->nrows;
+      if (h->split) {
+        e = cudaMalloc(&h->d_rowmap, sizeof(int32_t) * (size_t)(h->nfull > 0 ? h->nfull : 1));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_trivlist, sizeof(int32_t) * (size_t)(h->ntriv > 0 ? h->ntriv : 1));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_nn_full, sizeof(int32_t) * (size_t)(h->nfull > 0 ? h->nfull : 1) * p);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_cond_full, sizeof(uint64_t) * (size_t)(h->nfull > 0 ? h->nfull : 1));
+        if (e == cudaSuccess) {
+          scatter_rows_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(is_full, pos_full, h->nrows, h->d_rowmap);
+          scatter_rows_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(is_triv, pos_triv, h->nrows, h->d_trivlist);
+          g_launches += 2;
+          if (h->nfull > 0) {
+            gather_nn_rows_kernel<<<grid_for(h->nfull * p, 256), 256, 0, h->stream>>>(h->d_nn, h->d_rowmap, h->nfull, p, h->d_nn_full);
+            g_launches++;
+          }
+          e = cudaStreamSynchronize(h->stream);
+        }
+      }
+    }
+    cudaFree(is_full); cudaFree(is_triv); cudaFree(pos_full); cudaFree(pos_triv); cudaFree(scan2);
     cudaFree(tmp); cudaFree(n0); cudaFree(scan_tmp);
     H_TRY(e);
     h->packed_len = last_off + last_n0;
@@ -616,8 +759,11 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
                               cudaStream_t st, int* nblocks_out) {
   UParams& q = cs->q;
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
-  q.nsets = h->nrows; q.rowmap = nullptr;
-  q.locs = h->d_locs; q.nn = h->d_nn; q.cond = h->d_cond; q.nuggets = d_nuggets;
+  q.nsets = h->split ? h->nfull : h->nrows;
+  q.rowmap = h->split ? h->d_rowmap : nullptr;
+  q.locs = h->d_locs; q.nuggets = d_nuggets;
+  q.nn = h->split ? h->d_nn_full : h->d_nn;
+  q.cond = h->split ? h->d_cond_full : h->d_cond;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
   q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
   q.partials = want_loglik ? h->d_partials : nullptr;
@@ -626,7 +772,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   const KernelEntry* e = general ? h->entry_gen : h->entry;
   const int cap = general ? h->max_blocks_gen : h->num_sms * h->blocks_per_sm;
   const int sets_per_block = kWarpsPerBlock * (32 / e->G);
-  int64_t want = (h->nrows + sets_per_block - 1) / sets_per_block;
+  int64_t want = (q.nsets + sets_per_block - 1) / sets_per_block;
   int cap_eff = cap;
   if (const char* env = std::getenv("GPV_BLOCKS_PER_SM")) {      // development knob: occupancy experiments
     const int b = std::atoi(env);
@@ -641,9 +787,19 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   g_launches++;
   CUDA_TRY(cudaEventRecord(h->ev_stop, st));
   CUDA_TRY(cudaGetLastError());
+  int total_blocks = blocks;
+  if (h->split && h->ntriv > 0) {
+    int64_t wt = (h->ntriv + 255) / 256;
+    const int tb = (int)(wt < kTrivBlocks ? wt : kTrivBlocks);
+    trivial_rows_kernel<<<tb, 256, 0, st>>>(q, h->d_nn, h->d_cond, h->d_trivlist, h->ntriv,
+                                             want_loglik ? h->d_partials + 2 * (size_t)blocks : nullptr);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    total_blocks += tb;
+  }
   h->ev_valid = true;
   h->last_kernel = e->name;
-  if (nblocks_out) *nblocks_out = blocks;
+  if (nblocks_out) *nblocks_out = total_blocks;
   return GPV_OK;
 }
 
