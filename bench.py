@@ -26,10 +26,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_PER_GPU = 1_000_000
-M = 30
-D = 2
-NU = 1.5
 SIG2 = 1.0
 
 
@@ -112,24 +108,41 @@ class ClockSampler(threading.Thread):
                     source="nvml" if self._nvml is not None else "nvidia-smi")
 
 
-def make_inputs(n_total, row_begin, row_end, device, use_gpu_nn=True):
+WORKLOADS = {
+    # name: (n per GPU or total, scaling, d, m, covType, covparms builder, cov tag for the flop count)
+    "cfg2": dict(n=1_000_000, scaling="weak", d=2, m=30, covType="matern", nu=1.5, tag="nu1.5",
+                 doc="BASELINE configs[1]: createU, 2-D, m=30, Matern nu=1.5 closed form, 1e6 rows per GPU"),
+    "cfg3": dict(n=10_000_000, scaling="strong", d=2, m=30, covType="matern", nu=0.8, tag="general",
+                 doc="BASELINE configs[2]: n=1e7 total, general-nu Matern (nu=0.8), rows sharded over the GPUs"),
+    "cfg4": dict(n=4_000_000, scaling="strong", d=3, m=40, covType="esqe", nu=None, tag="esqe",
+                 doc="BASELINE configs[3]: n=4e6 total 3-D, m=40 (one set per warp), esqe covariance"),
+}
+
+
+def make_inputs(wl, n_total, row_begin, row_end, device, use_gpu_nn=True):
     from gpvecchia_b200 import harness as H
-    locs = H.make_locs(n_total, D, stream=2)
+    d, m = wl["d"], wl["m"]
+    locs = H.make_locs(n_total, d, stream=2)
     if use_gpu_nn:
-        revNN = H.ordered_nn_gpu(locs, M, row_begin, row_end, device=device)
+        revNN = H.ordered_nn_gpu(locs, m, row_begin, row_end, device=device)
     else:
-        revNN = H.rev(H.ordered_nn_kdtree(locs, M, row_begin, row_end)).astype(np.int32)
+        revNN = H.rev(H.ordered_nn_kdtree(locs, m, row_begin, row_end)).astype(np.int32)
     # 'z' conditioning: neighbours on the response, self on the latent (vecchia_specify.R:189-190)
     revCond = np.zeros(revNN.shape, dtype=np.int32)
     revCond[revNN == 0] = np.iinfo(np.int32).min
     revCond[:, -1] = 1
     nuggets = H.make_nuggets(n_total, stream=2)
     z = H.make_data(n_total, stream=2)
-    covparms = np.array([SIG2, H.default_range(n_total, D), NU])
+    rng_ = H.default_range(n_total, d)
+    if wl["covType"] == "matern":
+        covparms = np.array([SIG2, rng_, wl["nu"]])
+    else:
+        covparms = np.array([1.0, rng_, 0.5, rng_])
     return locs, revNN, revCond, nuggets, z, covparms
 
 
-def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None):
+def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None,
+                       covType="matern"):
     """Times the restated reference (oracle/: OpenMP schedule(static) + LAPACK dpotrf/dtrtrs) on a
     bounded sample of the same workload's rows; returns (sets/s, threads, sample description)."""
     import oracle as O
@@ -139,7 +152,7 @@ def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covpa
 
     def timed(nrows_s):
         pr = O.RowsProblem(locs, revNN_rows[nr - nrows_s:], revCond_rows[nr - nrows_s:], row_begin + nr - nrows_s,
-                           nuggets, "matern", covparms)
+                           nuggets, covType, covparms)
         t0 = time.perf_counter()
         pr.run(threads)
         return time.perf_counter() - t0
@@ -147,9 +160,12 @@ def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covpa
     timed(min(2000, nr))                      # thread-pool / page-fault warm-up
     t_p = timed(pilot)
     nrows_s = int(min(nr, max(pilot, pilot / t_p * target_s)))
-    t_s = timed(nrows_s)
+    # about target_s seconds of CPU work in total: repeat the pass when the rank has too few rows
+    passes = int(min(10, max(1, round(target_s / max(nrows_s * t_p / pilot, 1e-3)))))
+    t_s = sum(timed(nrows_s) for _ in range(passes))
     lo = row_begin + nr - nrows_s
-    return nrows_s / t_s, threads, f"rows [{lo},{lo + nrows_s}) of the n={n_total} workload, {t_s:.1f} s"
+    return (nrows_s * passes / t_s, threads,
+            f"rows [{lo},{lo + nrows_s}) of the n={n_total} workload x {passes} passes, {t_s:.1f} s of CPU time")
 
 
 def main():
@@ -158,7 +174,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the workload's n (per GPU if weak, total if strong)")
     ap.add_argument("--host-nn", action="store_true", help="build neighbour arrays with cKDTree on the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -167,21 +184,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_total = args.n_per_gpu * world
-    p = M + 1
-    workload = f"cfg2: createU/U_NZentries, n={n_total} uniform 2-D locs ({args.n_per_gpu}/GPU), m={M}, Matern nu={NU}, 'z' conditioning"
-    config = dict(workload=workload, n=n_total, m=M, d=D, covmodel="matern", nu=NU, cond_yz="z",
-                  sharding=f"rows by contiguous range over {world} rank(s); locs replicated",
-                  l2="inputs+outputs per step (idx 124 MB + U 248 MB per 1e6 rows) exceed the 126 MB L2")
+    wl = dict(WORKLOADS[args.workload])
+    if args.n:
+        wl["n"] = args.n
+    n_total = wl["n"] * world if wl["scaling"] == "weak" else wl["n"]
+    m, d = wl["m"], wl["d"]
+    p = m + 1
+    cov_desc = f"Matern nu={wl['nu']}" if wl["covType"] == "matern" else "esqe"
+    workload = (f"{args.workload}: createU/U_NZentries, n={n_total} uniform {d}-D locs"
+                f"{' (' + str(wl['n']) + '/GPU)' if wl['scaling'] == 'weak' else ''}, m={m}, {cov_desc}, 'z' conditioning")
+    per_row_mb = (p * 4 + p * 8) / 1e6
+    config = dict(workload=workload, n=n_total, m=m, d=d, covmodel=wl["covType"], nu=wl["nu"], cond_yz="z",
+                  sharding=f"rows by contiguous range over {world} rank(s); locs and nuggets replicated",
+                  l2=f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank, larger than the 126 MB L2")
 
     if args.impl == "reference":
-        # ---- CPU arm: the restated reference on this box's host cores, rank 0 only ----------------
+        # ---- CPU arm: the restated reference (oracle/: OpenMP + LAPACK) on this box's host cores -----
         if rank != 0:
             return
         import oracle as O
         from gpvecchia_b200 import harness as H
         n_s = min(n_total, 400_000)      # neighbour arrays for a bounded sample of the workload's rows
-        locs = H.make_locs(n_total, D, stream=2)
+        locs = H.make_locs(n_total, d, stream=2)
         rb, re_ = n_total - n_s, n_total
         try:
             import gpvecchia_b200 as G
@@ -189,19 +213,19 @@ def main():
         except Exception:
             have_gpu = False
         if have_gpu and not args.host_nn:
-            revNN = H.ordered_nn_gpu(locs, M, rb, re_, device=0)
+            revNN = H.ordered_nn_gpu(locs, m, rb, re_, device=0)
         else:
-            revNN = H.rev(H.ordered_nn_kdtree(locs, M, rb, re_)).astype(np.int32)
+            revNN = H.rev(H.ordered_nn_kdtree(locs, m, rb, re_)).astype(np.int32)
         revCond = np.zeros(revNN.shape, dtype=np.int32)
         revCond[revNN == 0] = np.iinfo(np.int32).min
         revCond[:, -1] = 1
         nuggets = H.make_nuggets(n_total, stream=2)
-        covparms = np.array([SIG2, H.default_range(n_total, D), NU])
+        rng_ = H.default_range(n_total, d)
+        covparms = np.array([SIG2, rng_, wl["nu"]]) if wl["covType"] == "matern" else np.array([1.0, rng_, 0.5, rng_])
         threads = O.max_threads()
-        # size one step to ~3 s of CPU work
-        rate0, _, _ = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, target_s=2.0)
-        rows_step = int(min(n_s, max(10000, rate0 * 3.0)))
-        pr = O.RowsProblem(locs, revNN[-rows_step:], revCond[-rows_step:], re_ - rows_step, nuggets, "matern", covparms)
+        rate0, _, _ = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, target_s=2.0, covType=wl["covType"])
+        rows_step = int(min(n_s, max(10000, rate0 * 3.0)))      # ~3 s of CPU work per step
+        pr = O.RowsProblem(locs, revNN[-rows_step:], revCond[-rows_step:], re_ - rows_step, nuggets, wl["covType"], covparms)
         for _ in range(args.warmup):
             pr.run(threads)
         t0 = time.perf_counter()
@@ -214,7 +238,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": value, "unit": "sets/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,11 +262,12 @@ def main():
     rb, re_ = int(cuts[rank]), int(cuts[rank + 1])
     nrows = re_ - rb
     t_gen = time.perf_counter()
-    locs, revNN, revCond, nuggets, z, covparms = make_inputs(n_total, rb, re_, local_rank, use_gpu_nn=not args.host_nn)
+    locs, revNN, revCond, nuggets, z, covparms = make_inputs(wl, n_total, rb, re_, local_rank, use_gpu_nn=not args.host_nn)
     t_gen = time.perf_counter() - t_gen
     obs = np.ones(n_total, dtype=np.int32)
-    h = G.UHandle(locs, revNN_full(revNN, rb, n_total), revCond_full(revCond, rb, n_total), obs=obs,
-                  row_begin=rb, row_end=re_, device=local_rank)
+    # each rank hands over only its own rows of revNNarray / revCond (gpv_create_shard)
+    h = G.UHandle(locs, revNN, revCond, obs=obs, row_begin=rb, row_end=re_, device=local_rank)
+    covType = wl["covType"]
 
     d_nug = torch.from_numpy(nuggets).to(dev)
     d_out = torch.empty(nrows * p, dtype=torch.float64, device=dev)
@@ -256,7 +281,7 @@ def main():
     assert stream != 0
 
     def step_dev():
-        h.u_dev("matern", covparms, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
+        h.u_dev(covType, covparms, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
 
     def barrier():
         if world > 1:
@@ -267,6 +292,7 @@ def main():
         for _ in range(warmup):
             fn()
         barrier()
+        h.kernel_time_stats(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -285,23 +311,21 @@ def main():
     launches = int(G.lib.gpv_launch_count() - launches0) - 2 * args.warmup
     clocks = sampler.stop()
     value = n_total * args.steps / (ms_total * 1e-3)
-
-    # kernel-only duration of the dominant kernel, CUDA events on the launching stream (library side)
-    kms = []
-    for _ in range(max(5, args.steps)):
-        step_dev()
-        kms.append(h.last_kernel_ms())
-    k_ms = float(np.mean(kms))
+    # duration of the dominant kernel over the SAME timed region: one CUDA-event pair per launch,
+    # recorded by the library on the launching stream
+    k_count, k_total = h.kernel_time_stats(reset=True)
+    k_ms = k_total / max(k_count, 1)
     kname = h.last_kernel_name()
 
     # ---- e2e: the reference-facing host-buffer call createU() makes --------------------------------
     total_packed = h.packed_len
-    host_out = torch.empty(total_packed + 2 * n_total, dtype=torch.float64).pin_memory()
+    n_obs = n_total
+    host_out = torch.empty(total_packed + 2 * n_obs, dtype=torch.float64).pin_memory()
     host_nug = torch.from_numpy(nuggets).pin_memory()
     out_np, nug_np = host_out.numpy(), host_nug.numpy()
 
     def step_e2e():
-        h.values_packed("matern", covparms, nug_np, nug_np, zentries_tail=True, out=out_np)
+        h.values_packed(covType, covparms, nug_np, nug_np, zentries_tail=True, out=out_np)
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -315,36 +339,41 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = n_total * e2e_steps / float(t_e2e.item())
-    h2d = 8 * n_total + 8 * n_total
-    d2h = 8 * (total_packed + 2 * n_total)
+    h2d = 8 * n_total + 8 * n_obs
+    d2h = 8 * (total_packed + 2 * n_obs)
 
     # ---- extras: loglik evals/sec (fused numerator, scalars out), other covariances ----------------
     extras = {}
     if not args.no_extras:
+        ll_steps = max(5, args.steps // 2)
+
         def step_ll():
-            h.u_dev("matern", covparms, d_nug.data_ptr(), None, d_zord=d_z.data_ptr(), d_loglik=d_ll.data_ptr(), stream=stream)
-        ms_ll = timed(step_ll, max(5, args.steps // 2), 3)
-        if world > 1:
-            shard.allreduce_loglik(d_ll)
-        extras["loglik_numerator_evals_per_s"] = (max(5, args.steps // 2)) / (ms_ll * 1e-3)
-        extras["loglik_numerator_sets_per_s"] = n_total * (max(5, args.steps // 2)) / (ms_ll * 1e-3)
-        per = {}
-        for tag, ct, cp in (("nu0.5", "matern", [SIG2, covparms[1], 0.5]), ("nu2.5", "matern", [SIG2, covparms[1], 2.5]),
-                            ("general_nu0.8", "matern", [SIG2, covparms[1], 0.8]),
-                            ("esqe", "esqe", [0.7, covparms[1], 0.3, covparms[1]])):
-            cpa = np.array(cp)
-            def fn(ct=ct, cpa=cpa):
-                h.u_dev(ct, cpa, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
-            ms = timed(fn, max(5, args.steps // 2), 3)
-            per[tag] = n_total * max(5, args.steps // 2) / (ms * 1e-3)
-        extras["sets_per_s_other_covariances"] = per
+            h.u_dev(covType, covparms, d_nug.data_ptr(), None, d_zord=d_z.data_ptr(), d_loglik=d_ll.data_ptr(), stream=stream)
+            if world > 1:
+                shard.allreduce_loglik(d_ll)          # 3 doubles over NCCL: the path's only collective
+        ms_ll = timed(step_ll, ll_steps, 3)
+        extras["loglik_numerator_evals_per_s"] = ll_steps / (ms_ll * 1e-3)
+        extras["loglik_numerator_sets_per_s"] = n_total * ll_steps / (ms_ll * 1e-3)
+        extras["loglik_numerator_last"] = [float(v) for v in d_ll.cpu().tolist()]
+        if args.workload == "cfg2":
+            per = {}
+            rng_ = float(covparms[1])
+            for tag, ct, cp in (("nu0.5", "matern", [SIG2, rng_, 0.5]), ("nu2.5", "matern", [SIG2, rng_, 2.5]),
+                                ("general_nu0.8", "matern", [SIG2, rng_, 0.8]), ("general_nu1.3", "matern", [SIG2, rng_, 1.3]),
+                                ("esqe", "esqe", [1.0, rng_, 0.5, rng_])):
+                cpa = np.array(cp)
+
+                def fn(ct=ct, cpa=cpa):
+                    h.u_dev(ct, cpa, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
+                ms = timed(fn, ll_steps, 3)
+                per[tag] = n_total * ll_steps / (ms * 1e-3)
+            extras["sets_per_s_other_covariances"] = per
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
-    F = flops_per_set(p, D, "nu1.5")
-    B = bytes_per_set(p, D)
+    F = flops_per_set(p, d, wl["tag"])
+    B = bytes_per_set(p, d)
     peak_tf = C.c_double(0)
     G._lib.check(G.lib.gpv_measure_fp64_peak(local_rank, C.byref(peak_tf)))
-    hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "MEASURED_PEAKS.json"
@@ -354,32 +383,36 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf.value,
-        "peak_source": "DFMA micro-kernel measured in this run (gpv_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
-        "flops_per_set": F, "sets_per_launch": nrows, "kernel_ms": k_ms,
+        "peak_source": "fp64 FMA peak from a DFMA micro-kernel in this run (gpv_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has HBM and bf16 only",
+        "flops_per_set": F, "sets_per_launch": nrows, "kernel_ms": k_ms, "kernel_launches_timed": k_count,
+        "kernel_share_of_step": k_ms / (ms_total / args.steps),
         "hbm": {"achieved": B * nrows / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": B * nrows / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_set": B, "peak_source": hbm_src},
         "traffic": None,
     }
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "cfg2":
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            roofline["traffic"] = pj.get("dram_bytes_per_launch")
+            roofline["fp64_pipe_active_pct_ncu"] = pj.get("fp64_pipe_pct_of_peak_active")
         except Exception:
             pass
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, cores, sample = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms)
+        rate, cores, sample = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, covType=covType)
         cpu = {"value": rate, "unit": "sets/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
             "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "sets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": "gpv_u_values_packed (createU's U_NZentries + packing, host buffers, pinned)"},
+                    "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers)"},
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
             "input_generation_s": t_gen,
         }
@@ -387,23 +420,6 @@ def main():
     h.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def revNN_full(revNN_rows, rb, n_total):
-    """gpv_create takes whole column-major arrays (as R passes them); place the shard's rows."""
-    if revNN_rows.shape[0] == n_total:
-        return revNN_rows
-    full = np.zeros((n_total, revNN_rows.shape[1]), dtype=np.int32)
-    full[rb:rb + revNN_rows.shape[0]] = revNN_rows
-    return full
-
-
-def revCond_full(revCond_rows, rb, n_total):
-    if revCond_rows.shape[0] == n_total:
-        return revCond_rows
-    full = np.full((n_total, revCond_rows.shape[1]), np.iinfo(np.int32).min, dtype=np.int32)
-    full[rb:rb + revCond_rows.shape[0]] = revCond_rows
-    return full
 
 
 if __name__ == "__main__":

@@ -16,9 +16,9 @@ GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
 
 # every symbol include/gpvecchia_b200.h declares (tests check the .so exports all of them)
 EXPORTED = [
-    "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_destroy",
+    "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_create_shard", "gpv_destroy",
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
-    "gpv_loglik_numerator", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_last_kernel_name",
+    "gpv_loglik_numerator", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
 ]
@@ -44,6 +44,10 @@ def _load():
     L.gpv_device_count.restype = i32
     L.gpv_create.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, i64, i64, i32]
     L.gpv_create.restype = i32
+    L.gpv_create_shard.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, i64, i64, i32]
+    L.gpv_create_shard.restype = i32
+    L.gpv_kernel_time_stats.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(dbl)]
+    L.gpv_kernel_time_stats.restype = i32
     L.gpv_destroy.argtypes = [vp]
     L.gpv_destroy.restype = None
     L.gpv_set_revcond.argtypes = [vp, vp, i32]

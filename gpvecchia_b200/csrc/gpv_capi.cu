@@ -93,14 +93,14 @@ const KernelEntry* select_kernel(int p, int d, bool general) {
 // ------------------------------------------------------------------------------------------------
 // column-major 1-based revNN (0 = missing) -> row-major 0-based (-1 = missing), shard rows only;
 // also per-row n0.
-__global__ void prep_nn_kernel(const int32_t* __restrict__ nn_cm, int64_t Nlocs, int p,
+__global__ void prep_nn_kernel(const int32_t* __restrict__ nn_cm, int64_t ld, int p,
                                int64_t row_begin, int64_t nrows, int32_t* __restrict__ nn_rm,
                                int64_t* __restrict__ n0_out) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
   int n0 = 0;
   for (int j = 0; j < p; ++j) {
-    const int32_t v = nn_cm[(row_begin + r) + (int64_t)j * Nlocs];
+    const int32_t v = nn_cm[(row_begin + r) + (int64_t)j * ld];
     nn_rm[r * p + j] = v - 1;           // 0 -> -1 (missing)
     n0 += (v != 0);
   }
@@ -201,13 +201,13 @@ __device__ inline bool cond_is_true<double>(double v) { return v == 1.0; }
 // value other than 0/1 would scale the nugget; R can only pass 0/1/NA here (logical), NA rows are
 // never read (U_NZentries.cpp:47 reads the last n0 entries).
 template <typename T>
-__global__ void prep_cond_kernel(const T* __restrict__ cond_cm, int64_t Nlocs, int p,
+__global__ void prep_cond_kernel(const T* __restrict__ cond_cm, int64_t ld, int p,
                                  int64_t row_begin, int64_t nrows, uint64_t* __restrict__ mask) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
   uint64_t m = 0;
   for (int j = 0; j < p; ++j)
-    if (cond_is_true<T>(cond_cm[(row_begin + r) + (int64_t)j * Nlocs])) m |= (1ull << j);
+    if (cond_is_true<T>(cond_cm[(row_begin + r) + (int64_t)j * ld])) m |= (1ull << j);
   mask[r] = m;
 }
 __global__ void prep_locs_kernel(const double* __restrict__ locs_cm, int64_t Nlocs, int d,
@@ -363,6 +363,7 @@ struct gpv_handle {
   int64_t* d_row_off = nullptr;       // [nrows]
   int32_t* d_obsrank = nullptr;       // [Nlocs]
   // row split (only when >= 1/64 of the rows have n0 <= 1, e.g. `zy` layouts)
+  bool shard_arrays = false;          // revNN/revCond were given for the shard rows only
   bool split = false;
   int64_t nfull = 0, ntriv = 0;
   int32_t* d_rowmap = nullptr;        // [nfull] rows with n0 >= 2
@@ -390,7 +391,9 @@ struct gpv_handle {
   int blocks_per_sm = 0, num_sms = 0;
   int max_blocks_gen = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  static const int kRing = 128;
+  cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
+  int64_t n_launch = 0, stats_base = 0;
   bool ev_valid = false;
   const char* last_kernel = "";
 };
@@ -406,8 +409,10 @@ static void free_handle(gpv_handle* h) {
   cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
   cudaFree(h->d_first_fail); cudaFree(h->d_table);
-  if (h->ev_start) cudaEventDestroy(h->ev_start);
-  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  for (int i = 0; i < gpv_handle::kRing; ++i) {
+    if (h->ev_start[i]) cudaEventDestroy(h->ev_start[i]);
+    if (h->ev_stop[i]) cudaEventDestroy(h->ev_stop[i]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -417,12 +422,14 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 template <typename T>
 static gpv_status upload_cond(gpv_handle* h, const void* host) {
   T* tmp = nullptr;
-  const size_t bytes = sizeof(T) * (size_t)h->Nlocs * h->p;
+  const int64_t ld = h->shard_arrays ? h->nrows : h->Nlocs;
+  const size_t bytes = sizeof(T) * (size_t)ld * h->p;
   CUDA_TRY(cudaMalloc(&tmp, bytes));
   cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
-    prep_cond_kernel<T><<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, h->Nlocs, h->p,
-                                                                        h->row_begin, h->nrows, h->d_cond);
+    prep_cond_kernel<T><<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, ld, h->p,
+                                                                        h->shard_arrays ? 0 : h->row_begin,
+                                                                        h->nrows, h->d_cond);
     g_launches++;
     if (h->split && h->nfull > 0) {
       gather_cond_rows_kernel<<<grid_for(h->nfull, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap, h->nfull,
@@ -445,10 +452,28 @@ extern "C" gpv_status gpv_set_revcond(gpv_handle* h, const void* revCond, gpv_co
   return fail(GPV_ERR_ARG, "gpv_set_revcond: unknown cond_type %d", (int)cond_type);
 }
 
+static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                              const int32_t* revNNarray, const void* revCond, gpv_cond_type cond_type,
+                              const int32_t* obs, int64_t row_begin, int64_t row_end, int device,
+                              bool shard_arrays);
+
 extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
                                  const int32_t* revNNarray, const void* revCond,
                                  gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
                                  int64_t row_end, int device) {
+  return create_impl(out, Nlocs, p, d, locs, revNNarray, revCond, cond_type, obs, row_begin, row_end, device, false);
+}
+extern "C" gpv_status gpv_create_shard(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                                       const int32_t* revNN_rows, const void* revCond_rows,
+                                       gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
+                                       int64_t row_end, int device) {
+  return create_impl(out, Nlocs, p, d, locs, revNN_rows, revCond_rows, cond_type, obs, row_begin, row_end, device, true);
+}
+
+static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                              const int32_t* revNNarray, const void* revCond, gpv_cond_type cond_type,
+                              const int32_t* obs, int64_t row_begin, int64_t row_end, int device,
+                              bool shard_arrays) {
   if (!out) return fail(GPV_ERR_ARG, "gpv_create: out is null");
   *out = nullptr;
   if (!locs || !revNNarray || !revCond) return fail(GPV_ERR_ARG, "gpv_create: null input array");
@@ -473,6 +498,7 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   h->row_begin = row_begin; h->row_end = row_end; h->nrows = row_end - row_begin;
   h->entry = entry;
   h->entry_gen = entry_gen;
+  h->shard_arrays = shard_arrays;
 #define H_TRY(expr)                                                                                 \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
@@ -488,8 +514,10 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   H_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
   H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  H_TRY(cudaEventCreate(&h->ev_start));
-  H_TRY(cudaEventCreate(&h->ev_stop));
+  for (int i = 0; i < gpv_handle::kRing; ++i) {
+    H_TRY(cudaEventCreate(&h->ev_start[i]));
+    H_TRY(cudaEventCreate(&h->ev_stop[i]));
+  }
   H_TRY(cudaFuncSetAttribute((const void*)entry->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              entry->smem_bytes));
   H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, (const void*)entry->kernel,
@@ -544,13 +572,14 @@ extern "C" gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, 
   if (h->nrows > 0) {
     int32_t* tmp = nullptr;
     int64_t* n0 = nullptr;
-    H_TRY(cudaMalloc(&tmp, sizeof(int32_t) * (size_t)Nlocs * p));
+    const int64_t ld = shard_arrays ? h->nrows : Nlocs;
+    H_TRY(cudaMalloc(&tmp, sizeof(int32_t) * (size_t)ld * p));
     cudaError_t e = cudaMalloc(&n0, sizeof(int64_t) * nr);
     void* scan_tmp = nullptr;
     size_t scan_bytes = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, revNNarray, sizeof(int32_t) * (size_t)Nlocs * p, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, revNNarray, sizeof(int32_t) * (size_t)ld * p, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-      prep_nn_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, Nlocs, p, row_begin, h->nrows, h->d_nn, n0);
+      prep_nn_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, ld, p, shard_arrays ? 0 : row_begin, h->nrows, h->d_nn, n0);
       g_launches++;
       e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, n0, h->d_row_off, (int)h->nrows, h->stream);
     }
@@ -659,8 +688,28 @@ extern "C" gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms) {
   if (!h || !ms) return fail(GPV_ERR_ARG, "gpv_last_kernel_ms: null argument");
   if (!h->ev_valid) return fail(GPV_ERR_ARG, "gpv_last_kernel_ms: no launch recorded yet");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaEventSynchronize(h->ev_stop));
-  CUDA_TRY(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+  const int slot = (int)((h->n_launch - 1) % gpv_handle::kRing);
+  CUDA_TRY(cudaEventSynchronize(h->ev_stop[slot]));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev_start[slot], h->ev_stop[slot]));
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_kernel_time_stats(gpv_handle* h, int reset, int64_t* count, double* total_ms) {
+  if (!h) return fail(GPV_ERR_ARG, "gpv_kernel_time_stats: null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int64_t first = h->stats_base;
+  if (h->n_launch - first > gpv_handle::kRing) first = h->n_launch - gpv_handle::kRing;
+  double tot = 0.0;
+  for (int64_t i = first; i < h->n_launch; ++i) {
+    const int slot = (int)(i % gpv_handle::kRing);
+    float ms = 0.f;
+    CUDA_TRY(cudaEventSynchronize(h->ev_stop[slot]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_start[slot], h->ev_stop[slot]));
+    tot += ms;
+  }
+  if (count) *count = h->n_launch - first;
+  if (total_ms) *total_ms = tot;
+  if (reset) h->stats_base = h->n_launch;
   return GPV_OK;
 }
 
@@ -782,10 +831,12 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   if (blocks < 1) blocks = 1;
   reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
   g_launches++;
-  CUDA_TRY(cudaEventRecord(h->ev_start, st));
+  const int slot = (int)(h->n_launch % gpv_handle::kRing);
+  CUDA_TRY(cudaEventRecord(h->ev_start[slot], st));
   e->kernel<<<blocks, kThreadsPerBlock, e->smem_bytes, st>>>(q);
   g_launches++;
-  CUDA_TRY(cudaEventRecord(h->ev_stop, st));
+  CUDA_TRY(cudaEventRecord(h->ev_stop[slot], st));
+  h->n_launch++;
   CUDA_TRY(cudaGetLastError());
   int total_blocks = blocks;
   if (h->split && h->ntriv > 0) {

@@ -74,17 +74,22 @@ class UHandle:
     """
 
     def __init__(self, locsord, revNNarray, revCond, obs=None, row_begin=0, row_end=None, device=0):
+        """revNNarray / revCond: either all N rows (as R holds them) or only the rows
+        [row_begin,row_end) of this shard (gpv_create_shard)."""
         locs = np.asarray(locsord, dtype=np.float64)
         if locs.ndim != 2:
             raise ValueError("Locations must be in matrix form")   # vecchia_specify.R:32-35
         self.N, self.d = locs.shape
         nn = _nn_to_i32(revNNarray)
-        if nn.shape[0] != self.N:
-            raise ValueError("revNNarray must have one row per location")
         self.p = nn.shape[1]
         self.row_begin = int(row_begin)
         self.row_end = self.N if row_end is None else int(row_end)
         self.nrows = self.row_end - self.row_begin
+        self._shard_arrays = nn.shape[0] != self.N
+        if self._shard_arrays and nn.shape[0] != self.nrows:
+            raise ValueError("revNNarray must have one row per location, or one per row of the shard")
+        if np.asarray(revCond).shape != nn.shape:
+            raise ValueError("revCond must have the shape of revNNarray")
         self.device = int(device)
         self.n_obs = 0
         obs_i32 = None
@@ -92,7 +97,8 @@ class UHandle:
             obs_i32 = np.ascontiguousarray(np.asarray(obs).astype(bool).astype(np.int32))
             self.n_obs = int(obs_i32.sum())
         h = C.c_void_p()
-        check(lib.gpv_create(C.byref(h), self.N, self.p, self.d, _ptr(_colmajor(locs, np.float64)),
+        create = lib.gpv_create_shard if self._shard_arrays else lib.gpv_create
+        check(create(C.byref(h), self.N, self.p, self.d, _ptr(_colmajor(locs, np.float64)),
                              _ptr(_colmajor(nn, np.int32)),
                              _ptr(_colmajor(_cond_to_rlogical(revCond), np.int32)),
                              _lib.GPV_COND_RLOGICAL_I32, _ptr(obs_i32), self.row_begin, self.row_end,
@@ -183,6 +189,13 @@ class UHandle:
         ms = C.c_float(0)
         check(lib.gpv_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def kernel_time_stats(self, reset=True):
+        """(launch count, total ms) of the set kernel since the last reset, from per-launch CUDA
+        events recorded on the launching stream inside the library."""
+        cnt, tot = C.c_int64(0), C.c_double(0.0)
+        check(lib.gpv_kernel_time_stats(self._h, 1 if reset else 0, C.byref(cnt), C.byref(tot)))
+        return int(cnt.value), float(tot.value)
 
     def last_kernel_name(self):
         return lib.gpv_last_kernel_name(self._h).decode()

@@ -68,6 +68,12 @@ gpv_status gpv_create(gpv_handle** out, int64_t Nlocs, int p, int d, const doubl
                       const int32_t* revNNarray, const void* revCondOnLatent,
                       gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
                       int64_t row_end, int device);
+/* Same, but revNN_rows / revCond_rows hold ONLY the rows [row_begin,row_end) (column-major with
+ * leading dimension row_end - row_begin): what a rank of a multi-GPU job has after sharding. */
+gpv_status gpv_create_shard(gpv_handle** out, int64_t Nlocs, int p, int d, const double* locs,
+                            const int32_t* revNN_rows, const void* revCond_rows,
+                            gpv_cond_type cond_type, const int32_t* obs, int64_t row_begin,
+                            int64_t row_end, int device);
 void gpv_destroy(gpv_handle* h);
 
 /* Re-upload revCond (createU.R:83-86 rewrites it per call when some nuggets are zero). */
@@ -113,6 +119,9 @@ gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double* covparms,
 /* Milliseconds of the last U kernel launch of this handle, from CUDA events recorded on the
  * launching stream around that launch (synchronises on the stop event). */
 gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms);
+/* Sum of the set-kernel durations (CUDA events on the launching stream, one pair per launch, ring
+ * of 128) since the last reset: *count launches, *total_ms milliseconds. */
+gpv_status gpv_kernel_time_stats(gpv_handle* h, int reset, int64_t* count, double* total_ms);
 /* Name of the kernel instantiation the last launch used, e.g. "u_sets<P=32,D=2>". */
 const char* gpv_last_kernel_name(const gpv_handle* h);
 /* Number of kernels this library launched since load (monotone counter; bench's gpu_launches). */

@@ -381,3 +381,27 @@ def test_cfg5_obs_pred_joint_ordering_zy():
     q, l, _ = G.vecchia_loglik_numerator(z, va, cp, tau)
     qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
     assert abs(q - qr) <= LL_TOL * abs(qr) and abs(l - lr) <= LL_TOL * abs(lr)
+
+
+def test_shard_arrays_entry_point_and_kernel_timing():
+    # gpv_create_shard: a rank hands over only its own rows of revNNarray / revCond
+    n, m = 2500, 9
+    va = _problem(n, m, 2, "z", stream=95)
+    prep = va["U_prep"]
+    nug = H.make_nuggets(n, stream=95)
+    z = H.make_data(n, stream=95)
+    obs = np.ones(n, dtype=bool)
+    cp = [1.0, 0.05, 2.5]
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=obs) as h:
+        full = h.U_NZentries("matern", cp, nug, nug)["Lentries"]
+        q, l, _ = h.loglik_numerator("matern", cp, nug, nug, z)
+        cnt, tot = h.kernel_time_stats()
+        assert cnt == 2 and tot > 0
+    a, b = 700, 1900
+    with G.UHandle(va["locsord"], prep["revNNarray"][a:b], prep["revCond"][a:b], obs=obs, row_begin=a, row_end=b) as hs:
+        part = hs.U_NZentries("matern", cp, nug, nug)["Lentries"]
+        assert np.array_equal(part, full[a:b])
+        packed, _, _ = hs.values_packed("matern", cp, nug, nug, zentries_tail=False)
+        assert packed.size == (b - a) * (m + 1) and np.array_equal(packed, full[a:b].ravel())
+    with pytest.raises(ValueError):
+        G.UHandle(va["locsord"], prep["revNNarray"][a:b], prep["revCond"][a:b], obs=obs, row_begin=a, row_end=b + 5)
