@@ -141,12 +141,22 @@ def make_inputs(wl, n_total, row_begin, row_end, device, use_gpu_nn=True):
     return locs, revNN, revCond, nuggets, z, covparms
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so
+    omp_get_max_threads() would understate the box; the oracle takes the team size as an argument
+    (num_threads(Ncores), like src/U_NZentries.cpp:37)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None,
                        covType="matern"):
     """Times the restated reference (oracle/: OpenMP schedule(static) + LAPACK dpotrf/dtrtrs) on a
     bounded sample of the same workload's rows; returns (sets/s, threads, sample description)."""
     import oracle as O
-    threads = threads or O.max_threads()
+    threads = threads or host_threads()
     n_total = locs.shape[0]
     nr = revNN_rows.shape[0]
 
@@ -222,7 +232,7 @@ def main():
         nuggets = H.make_nuggets(n_total, stream=2)
         rng_ = H.default_range(n_total, d)
         covparms = np.array([SIG2, rng_, wl["nu"]]) if wl["covType"] == "matern" else np.array([1.0, rng_, 0.5, rng_])
-        threads = O.max_threads()
+        threads = host_threads()
         rate0, _, _ = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, target_s=2.0, covType=wl["covType"])
         rows_step = int(min(n_s, max(10000, rate0 * 3.0)))      # ~3 s of CPU work per step
         pr = O.RowsProblem(locs, revNN[-rows_step:], revCond[-rows_step:], re_ - rows_step, nuggets, wl["covType"], covparms)
