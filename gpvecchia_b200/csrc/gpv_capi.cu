@@ -391,6 +391,13 @@ struct gpv_handle {
   int blocks_per_sm = 0, num_sms = 0;
   int max_blocks_gen = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  // chunked packed-output pipeline (kernel of chunk c+1 overlaps the D2H copy of chunk c)
+  static const int kChunks = 16;
+  int nchunks = 0;
+  int64_t chunk_set[kChunks + 1] = {};   // first set of each chunk
+  int64_t chunk_out[kChunks + 1] = {};   // packed output offset where each chunk's rows start
+  cudaEvent_t chunk_done[kChunks] = {};
   static const int kRing = 128;
   cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
   int64_t n_launch = 0, stats_base = 0;
@@ -413,6 +420,8 @@ static void free_handle(gpv_handle* h) {
     if (h->ev_start[i]) cudaEventDestroy(h->ev_start[i]);
     if (h->ev_stop[i]) cudaEventDestroy(h->ev_stop[i]);
   }
+  for (int i = 0; i < gpv_handle::kChunks; ++i) if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -514,6 +523,8 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
   H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  H_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < gpv_handle::kChunks; ++i) H_TRY(cudaEventCreateWithFlags(&h->chunk_done[i], cudaEventDisableTiming));
   for (int i = 0; i < gpv_handle::kRing; ++i) {
     H_TRY(cudaEventCreate(&h->ev_start[i]));
     H_TRY(cudaEventCreate(&h->ev_stop[i]));
@@ -673,6 +684,25 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     h->n_obs = (int64_t)last_e + last_f;
     h->have_obs = true;
   }
+  // chunk table for the overlapped packed-output call: sets are in increasing row order, so chunk c
+  // owns the packed values of rows [first row of chunk c, first row of chunk c+1)
+  {
+    const int64_t nsets = h->split ? h->nfull : h->nrows;
+    int nc = (int)(nsets / 32768);
+    if (nc > gpv_handle::kChunks) nc = gpv_handle::kChunks;
+    if (nc < 1) nc = 1;
+    h->nchunks = nc;
+    for (int c = 0; c <= nc; ++c) h->chunk_set[c] = nsets * c / nc;
+    h->chunk_out[0] = 0;
+    h->chunk_out[nc] = h->packed_len;
+    for (int c = 1; c < nc; ++c) {
+      int32_t row = (int32_t)h->chunk_set[c];
+      if (h->split) H_TRY(cudaMemcpy(&row, h->d_rowmap + h->chunk_set[c], sizeof(int32_t), cudaMemcpyDeviceToHost));
+      int64_t off = 0;
+      H_TRY(cudaMemcpy(&off, h->d_row_off + row, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      h->chunk_out[c] = off;
+    }
+  }
   *out = h;
   gpv_status st = gpv_set_revcond(h, revCond, cond_type);
   if (st != GPV_OK) { free_handle(h); *out = nullptr; return st; }
@@ -803,16 +833,23 @@ static gpv_status ensure_table(gpv_handle* h, CovSetup* cs, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // launch of the set kernel
 // ------------------------------------------------------------------------------------------------
+// set_begin/set_count select a chunk of the handle's sets (set_count < 0: all of them).  The
+// closed-form kernel for the n0 <= 1 rows runs with the first chunk only; likelihood partial sums
+// are only supported for whole-range launches.
 static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nuggets, double* d_out,
                               int packed, const double* d_zord, int64_t skip_rows, bool want_loglik,
-                              cudaStream_t st, int* nblocks_out) {
+                              cudaStream_t st, int* nblocks_out, int64_t set_begin = 0,
+                              int64_t set_count = -1) {
   UParams& q = cs->q;
+  const int64_t all_sets = h->split ? h->nfull : h->nrows;
+  if (set_count < 0) set_count = all_sets - set_begin;
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
-  q.nsets = h->split ? h->nfull : h->nrows;
-  q.rowmap = h->split ? h->d_rowmap : nullptr;
+  q.nsets = set_count;
+  q.set_base = set_begin;
+  q.rowmap = h->split ? h->d_rowmap + set_begin : nullptr;
   q.locs = h->d_locs; q.nuggets = d_nuggets;
-  q.nn = h->split ? h->d_nn_full : h->d_nn;
-  q.cond = h->split ? h->d_cond_full : h->d_cond;
+  q.nn = (h->split ? h->d_nn_full : h->d_nn) + set_begin * h->p;
+  q.cond = (h->split ? h->d_cond_full : h->d_cond) + set_begin;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
   q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
   q.partials = want_loglik ? h->d_partials : nullptr;
@@ -829,8 +866,10 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   }
   int blocks = (int)(want < (int64_t)cap_eff ? want : (int64_t)cap_eff);
   if (blocks < 1) blocks = 1;
-  reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
-  g_launches++;
+  if (set_begin == 0) {
+    reset_scalars_kernel<<<1, 1, 0, st>>>(h->d_nfail, h->d_first_fail);
+    g_launches++;
+  }
   const int slot = (int)(h->n_launch % gpv_handle::kRing);
   CUDA_TRY(cudaEventRecord(h->ev_start[slot], st));
   e->kernel<<<blocks, kThreadsPerBlock, e->smem_bytes, st>>>(q);
@@ -839,7 +878,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   h->n_launch++;
   CUDA_TRY(cudaGetLastError());
   int total_blocks = blocks;
-  if (h->split && h->ntriv > 0) {
+  if (h->split && h->ntriv > 0 && set_begin == 0) {
     int64_t wt = (h->ntriv + 255) / 256;
     const int tb = (int)(wt < kTrivBlocks ? wt : kTrivBlocks);
     trivial_rows_kernel<<<tb, 256, 0, st>>>(q, h->d_nn, h->d_cond, h->d_trivlist, h->ntriv,
@@ -923,7 +962,24 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
   const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
-  if (h->nrows > 0) {
+  bool chunked = false;
+  if (h->nrows > 0 && packed && h->nchunks > 1) {
+    // overlapped pipeline: kernel of chunk c+1 (compute stream) runs while the packed values of
+    // chunk c travel to the host (copy stream).  The rows of a chunk are contiguous in the packed
+    // vector; the n0 <= 1 rows interleaved with them are written by the first launch.
+    chunked = true;
+    for (int c = 0; c < h->nchunks; ++c) {
+      s = launch_sets(h, &cs, h->d_nuggets, h->d_out, 1, nullptr, 0, false, h->stream, nullptr,
+                      h->chunk_set[c], h->chunk_set[c + 1] - h->chunk_set[c]);
+      if (s) return s;
+      CUDA_TRY(cudaEventRecord(h->chunk_done[c], h->stream));
+      CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+      const int64_t o0 = h->chunk_out[c], o1 = h->chunk_out[c + 1];
+      if (o1 > o0)
+        CUDA_TRY(cudaMemcpyAsync(out + o0, h->d_out + o0, sizeof(double) * (size_t)(o1 - o0),
+                                 cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+  } else if (h->nrows > 0) {
     s = launch_sets(h, &cs, h->d_nuggets, h->d_out, packed, nullptr, 0, false, h->stream, nullptr);
     if (s) return s;
   } else {
@@ -933,7 +989,7 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   const bool want_z = (n > 0) && (zout != nullptr || ztail);
   if (want_z) { s = run_zentries(h, nuggets_obsord, n); if (s) return s; }
   if (packed) {
-    if (h->packed_len > 0)
+    if (h->packed_len > 0 && !chunked)
       CUDA_TRY(cudaMemcpyAsync(out, h->d_out, sizeof(double) * (size_t)h->packed_len, cudaMemcpyDeviceToHost, h->stream));
     if (ztail && n > 0)
       CUDA_TRY(cudaMemcpyAsync(out + h->packed_len, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -951,6 +1007,7 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   }
   if (!packed && zout && n > 0)
     CUDA_TRY(cudaMemcpyAsync(zout, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  if (chunked) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
   return read_fail_info(h, nfail, first_fail);
 }
 

@@ -51,7 +51,8 @@ struct CovTable {
 
 struct UParams {
   int64_t nrows;          // rows of this shard
-  int64_t nsets;          // conditioning sets handed to the set kernel (<= nrows)
+  int64_t nsets;          // conditioning sets handed to this launch
+  int64_t set_base;       // index of the launch's first set (chunked launches); row = set_base + s if no rowmap
   const int32_t* rowmap;  // [nsets] shard-local row of each set, or nullptr (set s is row s)
   int64_t row0;           // global index of the first row of the shard
   int p;                  // actual set size m+1 (<= P)
@@ -418,7 +419,7 @@ u_sets_kernel(const UParams q) {
       if (gl == 0) {
         __pipeline_memcpy_async(meta, q.cond + sidx, 8);
         if (q.rowmap != nullptr) __pipeline_memcpy_async(metai, q.rowmap + sidx, 4);
-        else metai[0] = (int)sidx;
+        else metai[0] = (int)(q.set_base + sidx);
       }
     } else {
       raw[gl] = -1;

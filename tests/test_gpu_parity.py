@@ -405,3 +405,36 @@ def test_shard_arrays_entry_point_and_kernel_timing():
         assert packed.size == (b - a) * (m + 1) and np.array_equal(packed, full[a:b].ravel())
     with pytest.raises(ValueError):
         G.UHandle(va["locsord"], prep["revNNarray"][a:b], prep["revCond"][a:b], obs=obs, row_begin=a, row_end=b + 5)
+
+
+@pytest.mark.parametrize("layout", ["z", "zy"])
+def test_chunked_packed_pipeline_matches_single_launch(layout):
+    # gpv_u_values_packed overlaps kernel chunks with D2H copies once there are >= 65536 sets;
+    # the result must be bit-identical to the unchunked row-major output, also with the
+    # n0 <= 1 rows of a zy layout interleaved (set list + closed-form kernel)
+    n, m = 70000, 10
+    locs = H.make_locs(n, 2, stream=97)
+    if layout == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        nug_all = np.concatenate([H.make_nuggets(n, stream=97), np.zeros(n)])
+    else:
+        locs2, NN = locs, H.ordered_nn_kdtree(locs, m)
+        Cond, obs = H.layout_yz(NN, "z"), np.ones(n, dtype=bool)
+        nug_all = H.make_nuggets(n, stream=97)
+    revNN, revCond = H.rev(NN), H.rev(Cond)
+    tau = nug_all[:n]
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    with G.UHandle(locs2, revNN, revCond, obs=obs) as h:
+        r = h.U_NZentries("matern", cp, nug_all, tau)
+        packed, nf, _ = h.values_packed("matern", cp, nug_all, tau)
+    want = np.concatenate([r["Lentries"].ravel()[(revNN[:, ::-1] != 0).ravel()], r["Zentries"]])
+    assert nf == 0 and np.array_equal(packed, want)
+    # and against the oracle on a sample of rows
+    rows = np.r_[0:50, n - 50:n] if layout == "z" else np.r_[n:n + 50, 2 * n - 50:2 * n]
+    rc = revCond.astype(np.float64); rc[revCond < 0] = np.nan
+    for a, b in ((rows[0], rows[49] + 1), (rows[50], rows[99] + 1)):
+        pr = O.RowsProblem(locs2, revNN[a:b], rc[a:b], a, nug_all, "matern", np.array(cp))
+        pr.run(2)
+        ref = pr.Lentries()
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(r["Lentries"][a:b] - ref) / scale).max() < 1e-9
