@@ -23,18 +23,23 @@
 namespace gpv {
 
 #ifndef GPV_TAB_DEG
-#define GPV_TAB_DEG 11
+#define GPV_TAB_DEG 19
 #endif
 #ifndef GPV_TAB_SUBBITS
-#define GPV_TAB_SUBBITS 3
+#define GPV_TAB_SUBBITS 1
 #endif
 constexpr int kTabDeg = GPV_TAB_DEG;
 constexpr int kTabSubBits = GPV_TAB_SUBBITS;   // 2^bits intervals per octave of w
 constexpr int kTabSub = 1 << kTabSubBits;
 constexpr int kTabOctaves = 64;             // covered range of w below its maximum
-constexpr int kTabStride = kTabOctaves * kTabSub;   // fixed row stride: coefficient k of interval i
-                                                    // sits at coef[k * kTabStride + i] (immediate offsets)
-constexpr double kTabSSplit = 16.0;          // s >= split: table holds exp(s) * cov
+constexpr double kTabSSplit = 16.0;         // s >= split: table holds exp(s) * cov
+constexpr int kTabStride = kTabOctaves * kTabSub;   // intervals per coefficient row
+// Coefficient-major storage: coefficient k of interval i sits at coef[k * kTabStride + i] (every
+// offset an immediate).  The gather is bound by the L1 data pipe (94 % busy, profiles/): few, wide
+// intervals keep the lanes of a warp on few cache lines.  Measured at n = 1e6, m = 30 (ms per
+// launch): (sub_bits, degree) = (3,11) 5.50, (2,14) 5.34, (1,19) 5.14; 16-byte paired loads
+// (1,19) 5.57; interval-major rows (5,7) 7.03.
+__host__ __device__ constexpr int tab_coef_index(int k, int i) { return k * kTabStride + i; }
 
 __host__ __device__ inline int hi32_of(double x) {
 #ifdef __CUDA_ARCH__
@@ -215,36 +220,44 @@ __global__ void build_cov_table_kernel(CovTable t, double inv_range, double* coe
     cheb_fit_to_monomial(f, 1.0 / (double)(2 * kTabSub), mono);
     // coefficients are for v in mantissa units: w = 2^e * (mc + v) -> absorb nothing, f is a
     // function of the mantissa within a fixed octave, so no extra scaling is needed.
-    for (int k = 0; k < n; ++k) coef_out[(size_t)k * kTabStride + idx] = mono[k];
+    for (int k = 0; k < n; ++k) coef_out[tab_coef_index(k, idx)] = mono[k];
   }
 }
 #endif  // GPV_DEFINE_TABLE_BUILDER
 
-__device__ __forceinline__ double cov_general(double r2, const UParams& q, const double* __restrict__ etab) {
-  const CovTable& t = q.tab;
-  const int hi = __double2hiint(r2);
-  const int idx = (hi >> (20 - kTabSubBits)) - t.idx0;
-  const bool in_table = (unsigned)idx < (unsigned)t.nint;
-  double acc;
-  if (__all_sync(__activemask(), in_table || r2 == 0.0)) {
-    // common case, warp-uniform: every active lane is inside the table (or at distance 0)
-    const int lo = __double2loint(r2);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
-    const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
-    const double v = m - mc;
-    const double* cf = t.coef + (in_table ? idx : 0);
-    acc = __ldg(cf + kTabDeg * kTabStride);
+// Fast path: every lane of the warp is strictly inside the table and below the exp split.
+__device__ __forceinline__ double cov_general_fast(double r2, int idx, const CovTable& t) {
+  const int hi = __double2hiint(r2), lo = __double2loint(r2);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
+  const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
+  const double v = m - mc;
+  const double* cf = t.coef + idx;
+  double acc = __ldg(cf + kTabDeg * kTabStride);
 #pragma unroll
-    for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
-    if (__any_sync(__activemask(), r2 >= t.w_split)) {        // rare: far pairs of the first rows
-      if (r2 >= t.w_split) acc *= exp_neg(sqrt_pos(r2) * q.inv_range, etab);
-    }
-  } else {
-    // some lane is outside the table (or NaN/Inf/denormal): direct Temme / CF2 evaluation
-    acc = matern_general_direct(sqrt(r2) * q.inv_range, t);
-  }
-  return (r2 == 0.0) ? q.c0 : acc;                      // Matern.cpp:76-77
+  for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
+  return acc;
+}
+// Slow path (per lane correct for anything): zero distance, far pairs (exp split), arguments outside
+// the table, NaN.
+static __device__ __noinline__ double cov_general_slow(double r2, const UParams& q, const double* __restrict__ etab) {
+  const CovTable& t = q.tab;
+  if (r2 == 0.0) return q.c0;                                      // Matern.cpp:76-77
+  const int idx = (__double2hiint(r2) >> (20 - kTabSubBits)) - t.idx0;
+  if ((unsigned)idx >= (unsigned)t.nint) return matern_general_direct(sqrt(r2) * q.inv_range, t);
+  double acc = cov_general_fast(r2, idx, t);
+  if (r2 >= t.w_split) acc *= exp_neg(sqrt_pos(r2) * q.inv_range, etab);
+  return acc;
+}
+__device__ __forceinline__ bool cov_general_special(double r2, const CovTable& t, int* idx) {
+  *idx = (__double2hiint(r2) >> (20 - kTabSubBits)) - t.idx0;
+  return ((unsigned)*idx >= (unsigned)t.nint) || (r2 >= t.w_split);   // also catches 0, NaN, Inf
+}
+__device__ __forceinline__ double cov_general(double r2, const UParams& q, const double* __restrict__ etab) {
+  int idx;
+  const bool special = cov_general_special(r2, q.tab, &idx);
+  if (__any_sync(__activemask(), special)) return cov_general_slow(r2, q, etab);
+  return cov_general_fast(r2, idx, q.tab);
 }
 
 }  // namespace gpv

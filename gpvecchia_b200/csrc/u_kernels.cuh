@@ -207,6 +207,9 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ e
 // --------------------------------------------------------------------------------------------
 __device__ double matern_general_direct(double s, const CovTable& t);  // bessel_table.cuh
 __device__ __forceinline__ double cov_general(double r2, const UParams& q, const double* __restrict__ etab);
+__device__ __forceinline__ bool cov_general_special(double r2, const CovTable& t, int* idx);
+__device__ __forceinline__ double cov_general_fast(double r2, int idx, const CovTable& t);
+static __device__ __noinline__ double cov_general_slow(double r2, const UParams& q, const double* __restrict__ etab);
 
 template <int KIND>
 __device__ __forceinline__ double cov_eval(double r2, const UParams& q, const double* __restrict__ etab) {
@@ -330,8 +333,22 @@ __device__ __forceinline__ void pair_eval_store(const UParams& q, double* __rest
   const double guard = (KIND == COV_GENERAL) ? 0.0 : kMathC[7];
   const double r2l = pair_r2<D>(xs, LY::PX, xl, jl, d, guard);
   const double r2h = pair_r2<D>(xs, LY::PX, xh, jh, d, guard);
-  const double vl = cov_eval<KIND>(r2l, q, etab);
-  const double vh = cov_eval<KIND>(r2h, q, etab);
+  double vl, vh;
+  if (KIND == COV_GENERAL) {
+    // one warp-uniform decision for both evaluations of the iteration (the loop is convergent)
+    int idxl, idxh;
+    const bool sp = cov_general_special(r2l, q.tab, &idxl) | cov_general_special(r2h, q.tab, &idxh);
+    if (__any_sync(0xffffffffu, sp)) {
+      vl = cov_general_slow(r2l, q, etab);
+      vh = cov_general_slow(r2h, q, etab);
+    } else {
+      vl = cov_general_fast(r2l, idxl, q.tab);
+      vh = cov_general_fast(r2h, idxh, q.tab);
+    }
+  } else {
+    vl = cov_eval<KIND>(r2l, q, etab);
+    vh = cov_eval<KIND>(r2h, q, etab);
+  }
   As[offs & 0xffffu] = vl;
   As[offs >> 16] = vh;
 }
