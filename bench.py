@@ -282,7 +282,7 @@ def main():
     d_nug = torch.from_numpy(nuggets).to(dev)
     d_out = torch.empty(nrows * p, dtype=torch.float64, device=dev)
     d_z = torch.from_numpy(z).to(dev)
-    d_ll = torch.zeros(3, dtype=torch.float64, device=dev)
+    d_ll = torch.zeros(8, dtype=torch.float64, device=dev)
     # a dedicated (non-default) torch stream: its handle is what the C ABI launches on, and the
     # torch events below are recorded on the same stream
     tstream = torch.cuda.Stream(device=dev)
@@ -362,9 +362,15 @@ def main():
             if world > 1:
                 shard.allreduce_loglik(d_ll)          # 3 doubles over NCCL: the path's only collective
         ms_ll = timed(step_ll, ll_steps, 3)
-        extras["loglik_numerator_evals_per_s"] = ll_steps / (ms_ll * 1e-3)
-        extras["loglik_numerator_sets_per_s"] = n_total * ll_steps / (ms_ll * 1e-3)
-        extras["loglik_numerator_last"] = [float(v) for v in d_ll.cpu().tolist()]
+        # pure `z` layout: the same launch also accumulates the denominator terms, so this is the
+        # whole vecchia_likelihood (R/vecchia_likelihood.R:14-27) with the data resident in HBM
+        extras["loglik_evals_per_s"] = ll_steps / (ms_ll * 1e-3)
+        extras["loglik_sets_per_s"] = n_total * ll_steps / (ms_ll * 1e-3)
+        parts = [float(v) for v in d_ll.cpu().tolist()]
+        tau_terms = float(np.sum(z * z / nuggets)), float(np.sum(np.log(nuggets)))
+        qn, ldn, qd, ldd = parts[0] + tau_terms[0], parts[1] + tau_terms[1], parts[3], parts[4]
+        extras["loglik_value"] = -0.5 * (ldn - ldd + qn - qd + n_total * float(np.log(2 * np.pi)))
+        extras["loglik_parts"] = dict(quadform_num=qn, logdet_num=ldn, quadform_denom=qd, logdet_denom=ldd, nfail=parts[2])
         if args.workload == "cfg2":
             per = {}
             rng_ = float(covparms[1])

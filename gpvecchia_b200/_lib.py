@@ -18,7 +18,7 @@ GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
 EXPORTED = [
     "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_create_shard", "gpv_destroy",
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
-    "gpv_loglik_numerator", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
+    "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
 ]
@@ -60,6 +60,8 @@ def _load():
     L.gpv_u_values_packed.restype = i32
     L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
     L.gpv_loglik_numerator.restype = i32
+    L.gpv_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i32, vp]
+    L.gpv_loglik_z.restype = i32
     L.gpv_u_dev.argtypes = [vp, cp, vp, i32, vp, vp, i32, vp, i64, vp, vp]
     L.gpv_u_dev.restype = i32
     L.gpv_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]

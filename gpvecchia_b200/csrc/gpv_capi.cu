@@ -133,12 +133,27 @@ __global__ void gather_cond_rows_kernel(const uint64_t* __restrict__ cond, const
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nsets) cond_full[s] = cond[rowmap[s]];
 }
+// zloc[i] = z of location i (0 where unobserved): lets the set kernel gather z like a nugget
+__global__ void expand_z_kernel(const double* __restrict__ zord, const int32_t* __restrict__ obsrank,
+                                int64_t Nlocs, double* __restrict__ zloc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nlocs) return;
+  const int r = obsrank[i];
+  zloc[i] = r >= 0 ? zord[r] : 0.0;
+}
+// pure `z` conditioning: every non-missing neighbour is conditioned on the response, only self on
+// the latent (vecchia_specify.R:189-190) -> the row's mask is exactly the self bit
+__global__ void check_pure_z_kernel(const uint64_t* __restrict__ cond, int64_t nrows, int p,
+                                    int* __restrict__ not_pure) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows && cond[r] != (1ull << (p - 1))) atomicOr(not_pure, 1);
+}
 // one thread per row with n0 <= 1 (U_NZentries.cpp:39-69 with a 1x1 block; n0 == 0 rows stay zero)
 __global__ void trivial_rows_kernel(UParams q, const int32_t* __restrict__ nn_rows,
                                     const uint64_t* __restrict__ cond_rows, const int32_t* __restrict__ list,
                                     int64_t nlist, double* __restrict__ partials) {
-  __shared__ double red[8][2];
-  double acc_quad = 0.0, acc_logd = 0.0;
+  __shared__ double red[8][4];
+  double acc_quad = 0.0, acc_logd = 0.0, acc_qden = 0.0, acc_lden = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nlist;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = list[i];
@@ -168,25 +183,32 @@ __global__ void trivial_rows_kernel(UParams q, const int32_t* __restrict__ nn_ro
       }
     }
     if (partials != nullptr && id >= 0 && (q.row0 + row) >= q.skip_rows) {
-      double t = 0.0;
-      if (!condbit) { const int orank = q.obsrank[id]; if (orank >= 0) t = x * q.zord[orank]; }
+      const double t = condbit ? 0.0 : x * q.zloc[id];
       acc_quad += t * t;
       acc_logd += log(x);
+      if (q.full_z) {
+        const double tau = q.nuggets[id], zk = q.zloc[id];
+        const double w = fma(x, x, 1.0 / tau);
+        const double z2 = fma(x, t, -zk / tau);
+        acc_qden += z2 * z2 / w;
+        acc_lden += log(w);
+      }
     }
   }
   if (partials != nullptr) {
     for (int o = 16; o >= 1; o >>= 1) {
       acc_quad += __shfl_xor_sync(0xffffffffu, acc_quad, o);
       acc_logd += __shfl_xor_sync(0xffffffffu, acc_logd, o);
+      acc_qden += __shfl_xor_sync(0xffffffffu, acc_qden, o);
+      acc_lden += __shfl_xor_sync(0xffffffffu, acc_lden, o);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; }
+    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; red[warp][2] = acc_qden; red[warp][3] = acc_lden; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double s0 = 0, s1 = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s0 += red[w][0]; s1 += red[w][1]; }
-      partials[2 * blockIdx.x] = s0;
-      partials[2 * blockIdx.x + 1] = s1;
+    if (threadIdx.x < 4) {
+      double s0 = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s0 += red[w][threadIdx.x];
+      partials[4 * blockIdx.x + threadIdx.x] = s0;
     }
   }
 }
@@ -280,15 +302,19 @@ __global__ void obs_terms_kernel(const double* __restrict__ zord, const double* 
     partials[2 * blockIdx.x + 1] = s1;
   }
 }
-// out[0] = sum rows quad (+ obs quad), out[1] = -2 sum log x_self (+ sum log tau), out[2] = nfail.
+// out[0] = quadform.num, out[1] = logdet.num, out[2] = nfail, out[3] = quadform.denom,
+// out[4] = logdet.denom (the last two only for pure `z` layouts), all restricted to the shard.
 // Single thread, fixed order: run-to-run reproducible.
 __global__ void finalize_loglik_kernel(const double* __restrict__ row_partials, int nrow_blocks,
                                        const double* __restrict__ obs_partials, int nobs_blocks,
                                        const unsigned long long* __restrict__ nfail,
-                                       double* __restrict__ out) {
+                                       double* __restrict__ out, int nout) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double q = 0.0, l = 0.0;
-  for (int i = 0; i < nrow_blocks; ++i) { q += row_partials[2 * i]; l += row_partials[2 * i + 1]; }
+  double q = 0.0, l = 0.0, qd = 0.0, ld = 0.0;
+  for (int i = 0; i < nrow_blocks; ++i) {
+    q += row_partials[4 * i]; l += row_partials[4 * i + 1];
+    qd += row_partials[4 * i + 2]; ld += row_partials[4 * i + 3];
+  }
   double logdet = -2.0 * l;
   if (obs_partials != nullptr) {
     double qo = 0.0, lo = 0.0;
@@ -299,6 +325,7 @@ __global__ void finalize_loglik_kernel(const double* __restrict__ row_partials, 
   out[0] = q;
   out[1] = logdet;
   out[2] = (double)(*nfail);
+  if (nout > 3) { out[3] = qd; out[4] = -ld; }   // logdet.denom = -2 sum log diag(V) = -log det W
 }
 __global__ void reset_scalars_kernel(unsigned long long* nfail, long long* first_fail) {
   *nfail = 0ull;
@@ -374,6 +401,9 @@ struct gpv_handle {
   double* d_nuggets = nullptr;        // [Nlocs]
   double* d_tau = nullptr;            // [n_obs]
   double* d_zord = nullptr;           // [n_obs]
+  double* d_zloc = nullptr;           // [Nlocs] z per location for the fused likelihood
+  int* d_flag = nullptr;
+  bool pure_z = false;                // layout is pure `z` conditioning with every location observed
   double* d_out = nullptr;            // [nrows*p]
   double* d_out2 = nullptr;           // [nrows*p] (column-major copy) or packed + Z
   size_t out2_doubles = 0;
@@ -413,7 +443,7 @@ static void free_handle(gpv_handle* h) {
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
   cudaFree(h->d_obsrank); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
   cudaFree(h->d_trivlist); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
-  cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
+  cudaFree(h->d_zloc); cudaFree(h->d_flag); cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
   cudaFree(h->d_first_fail); cudaFree(h->d_table);
   for (int i = 0; i < gpv_handle::kRing; ++i) {
@@ -445,7 +475,13 @@ static gpv_status upload_cond(gpv_handle* h, const void* host) {
                                                                               h->d_cond_full);
       g_launches++;
     }
-    e = cudaStreamSynchronize(h->stream);
+    int not_pure = 0;
+    cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream);
+    check_pure_z_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(h->d_cond, h->nrows, h->p, h->d_flag);
+    g_launches++;
+    e = cudaMemcpyAsync(&not_pure, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    h->pure_z = (not_pure == 0) && h->have_obs && h->n_obs == h->Nlocs;
   }
   cudaFree(tmp);
   if (e != cudaSuccess) return fail(GPV_ERR_CUDA, "revCond upload failed: %s", cudaGetErrorString(e));
@@ -552,9 +588,10 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaMalloc(&h->d_cond, sizeof(uint64_t) * nr));
   H_TRY(cudaMalloc(&h->d_row_off, sizeof(int64_t) * nr));
   H_TRY(cudaMalloc(&h->d_nuggets, sizeof(double) * (size_t)Nlocs));
-  H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * (size_t)(h->max_blocks + kTrivBlocks)));
+  H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 4 * (size_t)(h->max_blocks + kTrivBlocks)));
+  H_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
   H_TRY(cudaMalloc(&h->d_obs_partials, sizeof(double) * 2 * kObsBlocks));
-  H_TRY(cudaMalloc(&h->d_loglik, sizeof(double) * 3));
+  H_TRY(cudaMalloc(&h->d_loglik, sizeof(double) * 8));
   H_TRY(cudaMalloc(&h->d_nfail, sizeof(unsigned long long)));
   H_TRY(cudaMalloc(&h->d_first_fail, sizeof(long long)));
 
@@ -851,7 +888,15 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.nn = (h->split ? h->d_nn_full : h->d_nn) + set_begin * h->p;
   q.cond = (h->split ? h->d_cond_full : h->d_cond) + set_begin;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
-  q.zord = d_zord; q.obsrank = h->d_obsrank; q.skip_rows = skip_rows;
+  q.zloc = nullptr; q.full_z = 0; q.skip_rows = skip_rows;
+  if (want_loglik) {
+    // z per location, expanded once per call so the set kernel can prefetch it like a nugget
+    if (!h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
+    expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, h->Nlocs, h->d_zloc);
+    g_launches++;
+    q.zloc = h->d_zloc;
+    q.full_z = (h->pure_z && skip_rows == 0) ? 1 : 0;
+  }
   q.partials = want_loglik ? h->d_partials : nullptr;
   q.nfail = h->d_nfail; q.first_fail = h->d_first_fail;
   const bool general = (q.cov == COV_GENERAL);
@@ -882,7 +927,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
     int64_t wt = (h->ntriv + 255) / 256;
     const int tb = (int)(wt < kTrivBlocks ? wt : kTrivBlocks);
     trivial_rows_kernel<<<tb, 256, 0, st>>>(q, h->d_nn, h->d_cond, h->d_trivlist, h->ntriv,
-                                             want_loglik ? h->d_partials + 2 * (size_t)blocks : nullptr);
+                                             want_loglik ? h->d_partials + 4 * (size_t)blocks : nullptr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     total_blocks += tb;
@@ -941,7 +986,7 @@ extern "C" gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double
   s = launch_sets(h, &cs, d_nuggets, d_out, packed, d_zord, skip_rows, d_loglik != nullptr, st, &nblocks);
   if (s) return s;
   if (d_loglik) {
-    finalize_loglik_kernel<<<1, 32, 0, st>>>(h->d_partials, nblocks, nullptr, 0, h->d_nfail, d_loglik);
+    finalize_loglik_kernel<<<1, 32, 0, st>>>(h->d_partials, nblocks, nullptr, 0, h->d_nfail, d_loglik, 5);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -1027,13 +1072,12 @@ extern "C" gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, co
                        nullptr, nfail, first_fail);
 }
 
-extern "C" gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, const double* covparms,
-                                           int ncov, const double* nuggets,
-                                           const double* nuggets_obsord, const double* zord, int64_t n,
-                                           int64_t skip_rows, int include_obs_terms, double out[3]) {
-  if (!h || !nuggets || !nuggets_obsord || !zord || !out) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: null argument");
-  if (!h->have_obs) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: handle was created without obs");
-  if (n != h->n_obs) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: n=%lld but sum(obs)=%lld", (long long)n, (long long)h->n_obs);
+static gpv_status loglik_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
+                                const double* nuggets, const double* nuggets_obsord, const double* zord,
+                                int64_t n, int64_t skip_rows, int include_obs_terms, double out5[5]) {
+  if (!h || !nuggets || !nuggets_obsord || !zord || !out5) return fail(GPV_ERR_ARG, "likelihood: null argument");
+  if (!h->have_obs) return fail(GPV_ERR_ARG, "likelihood: handle was created without obs");
+  if (n != h->n_obs) return fail(GPV_ERR_ARG, "likelihood: n=%lld but sum(obs)=%lld", (long long)n, (long long)h->n_obs);
   CUDA_TRY(cudaSetDevice(h->device));
   CovSetup cs;
   gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
@@ -1058,11 +1102,42 @@ extern "C" gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, c
   }
   finalize_loglik_kernel<<<1, 32, 0, h->stream>>>(h->d_partials, nblocks,
                                                   (obs_terms && n > 0) ? h->d_obs_partials : nullptr,
-                                                  kObsBlocks, h->d_nfail, h->d_loglik);
+                                                  kObsBlocks, h->d_nfail, h->d_loglik, 5);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(out, h->d_loglik, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(out5, h->d_loglik, sizeof(double) * 5, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, const double* covparms,
+                                           int ncov, const double* nuggets,
+                                           const double* nuggets_obsord, const double* zord, int64_t n,
+                                           int64_t skip_rows, int include_obs_terms, double out[3]) {
+  if (!out) return fail(GPV_ERR_ARG, "gpv_loglik_numerator: null argument");
+  double o5[5];
+  gpv_status s = loglik_common(h, covType, covparms, ncov, nuggets, nuggets_obsord, zord, n, skip_rows,
+                               include_obs_terms, o5);
+  if (s) return s;
+  out[0] = o5[0]; out[1] = o5[1]; out[2] = o5[2];
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_loglik_z(gpv_handle* h, const char* covType, const double* covparms, int ncov,
+                                   const double* nuggets, const double* nuggets_obsord, const double* zord,
+                                   int64_t n, int include_obs_terms, double out[6]) {
+  if (!h || !out) return fail(GPV_ERR_ARG, "gpv_loglik_z: null argument");
+  if (!h->pure_z)
+    return fail(GPV_ERR_UNSUPPORTED, "gpv_loglik_z: the layout is not pure `z` conditioning with every location "
+                                     "observed; use gpv_loglik_numerator and the reference's denominator");
+  double o5[5];
+  gpv_status s = loglik_common(h, covType, covparms, ncov, nuggets, nuggets_obsord, zord, n, 0,
+                               include_obs_terms, o5);
+  if (s) return s;
+  out[1] = o5[0]; out[2] = o5[1]; out[3] = o5[3]; out[4] = o5[4]; out[5] = o5[2];
+  // vecchia_likelihood.R:95-96 (meaningful when this handle holds every row; shards sum parts 1..4 first)
+  const double neg2 = out[2] - out[4] + out[1] - out[3] + (double)n * std::log(2.0 * 3.141592653589793238462643383279502884);
+  out[0] = -0.5 * neg2;
   return GPV_OK;
 }
 

@@ -63,10 +63,11 @@ struct UParams {
   const double* nuggets;  // [Nlocs]
   double* out;            // U values or nullptr
   const int64_t* row_off; // packed offsets [nrows] or nullptr (-> row*p, zero filled)
-  const double* zord;     // [n] or nullptr
-  const int32_t* obsrank; // [Nlocs] rank among observed locs or -1
+  const double* zloc;     // [Nlocs] z of each location (0 where unobserved) or nullptr: expanded per call from
+                          // zord / obsrank so the set kernel gathers it like a nugget
+  int full_z;             // 1: layout is pure `z` conditioning -> also accumulate the denominator terms
   int64_t skip_rows;      // global rows < skip_rows do not enter the likelihood sums
-  double* partials;       // [gridDim.x][2] or nullptr
+  double* partials;       // [gridDim.x][4] or nullptr: quad.num, sum log x_self, quad.denom, logdet.denom parts
   unsigned long long* nfail;
   long long* first_fail;
   int cov;                // CovKind
@@ -245,14 +246,15 @@ struct SetLayout {
   static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
   static constexpr int kX = DD * PX;                       // coordinates of the P points
   static constexpr int kNug = PX;                          // nuggets of the P points
+  static constexpr int kZ = PX;                            // z of the P points (likelihood only)
   static constexpr int kI = ((PX / 2 + 1) / 2) * 2;        // P int32 compacted ids (kept even)
   static constexpr int kRawI = G;                          // 2G int32 raw ids of a row (as stored)
   static constexpr int kMeta = 2;                          // cond mask (8 B), row (4 B), pad
   // one input stage = everything the pair stage and the epilogue read about a set; two of them so
   // that cp.async fills stage b^1 while stage b is being factored
-  static constexpr int kStage = kX + kNug + kI + kRawI + kMeta;
-  static constexpr int kOffNug = kX, kOffIds = kX + kNug, kOffRaw = kX + kNug + kI,
-                       kOffMeta = kX + kNug + kI + kRawI;
+  static constexpr int kStage = kX + kNug + kZ + kI + kRawI + kMeta;
+  static constexpr int kOffNug = kX, kOffZ = kX + kNug, kOffIds = kX + kNug + kZ,
+                       kOffRaw = kX + kNug + kZ + kI, kOffMeta = kX + kNug + kZ + kI + kRawI;
   static constexpr int kSetsPerWarp = 32 / G;
   // offset consecutive sets of a warp by 128/kSetsPerWarp bytes (mod 128) so that the per-set
   // broadcast loads of one warp instruction fall into different banks
@@ -419,7 +421,7 @@ u_sets_kernel(const UParams q) {
   const int rl = lowv ? gl : NLOW - 1;               // clamped row indices keep idle lanes in bounds
   const int rh = highv ? (P - 1 - gl) : (P - 1);
 
-  double acc_quad = 0.0, acc_logd = 0.0;
+  double acc_quad = 0.0, acc_logd = 0.0, acc_qden = 0.0, acc_lden = 0.0;
   const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock * SETS;
   const int64_t first = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * SETS;
 
@@ -476,6 +478,7 @@ u_sets_kernel(const UParams q) {
           for (int c = 0; c < d; ++c) __pipeline_memcpy_async(xs + c * PX + r, q.locs + (int64_t)id * d + c, 8);
         }
         __pipeline_memcpy_async(nug + r, q.nuggets + id, 8);
+        if (q.zloc != nullptr) __pipeline_memcpy_async(st + LY::kOffZ + r, q.zloc + id, 8);
       } else {
         if (D == 2) {
           reinterpret_cast<double2*>(xs)[r] = make_double2(0.0, 0.0);
@@ -661,22 +664,26 @@ u_sets_kernel(const UParams q) {
       }
     }
     if (q.partials != nullptr) {
-      // quadform: (sum_{j: revCond = 0} x_j * zord[obsrank(id_j)])^2 ; logdet: log x_self
+      // quadform.num: (sum_{j: revCond = 0} x_j z_j)^2 ; logdet.num: log x_self (vecchia_likelihood.R:74-76)
+      const double* zst = st + LY::kOffZ;
       double t = 0.0;
-      if (idl >= 0 && !cl) {
-        const int orank = q.obsrank[idl];
-        if (orank >= 0) t = xlow * q.zord[orank];
-      }
-      if (idh >= 0 && !ch) {
-        const int orank = q.obsrank[idh];
-        if (orank >= 0) t = fma(xhigh, q.zord[orank], t);
-      }
+      if (idl >= 0 && !cl) t = xlow * zst[rl];
+      if (idh >= 0 && !ch) t = fma(xhigh, zst[rh], t);
 #pragma unroll
       for (int o = G / 2; o >= 1; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
       const double xself = __shfl_sync(FULL, xhigh, base);     // row P-1 is lane 0's high row
       if (gl == 0 && row_ok && n0 > 0 && (q.row0 + row) >= q.skip_rows) {
         acc_quad += t * t;
         acc_logd += log(xself);
+        if (q.full_z) {
+          // pure `z` conditioning: U_y U_y^T is diagonal, W_kk = x_kk^2 + 1/tau_k, and
+          // z2_k = x_kk q_k - z_k / tau_k (vecchia_likelihood.R:85-91 per row)
+          const double tau = nugs[P - 1], zk = zst[P - 1];
+          const double w = fma(xself, xself, 1.0 / tau);
+          const double z2 = fma(xself, t, -zk / tau);
+          acc_qden += z2 * z2 / w;
+          acc_lden += log(w);
+        }
       }
     }
     __pipeline_wait_prior(0);                              // set i+1 staged, ids of set i+2 landed
@@ -687,19 +694,20 @@ u_sets_kernel(const UParams q) {
 
   // ---- deterministic block reduction of the likelihood partial sums ---------------------------------
   if (q.partials != nullptr) {
-    __shared__ double red[kWarpsPerBlock][2];
+    __shared__ double red[kWarpsPerBlock][4];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       acc_quad += __shfl_xor_sync(FULL, acc_quad, o);
       acc_logd += __shfl_xor_sync(FULL, acc_logd, o);
+      acc_qden += __shfl_xor_sync(FULL, acc_qden, o);
+      acc_lden += __shfl_xor_sync(FULL, acc_lden, o);
     }
-    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; }
+    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; red[warp][2] = acc_qden; red[warp][3] = acc_lden; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double a0 = 0.0, a1 = 0.0;
-      for (int w = 0; w < kWarpsPerBlock; ++w) { a0 += red[w][0]; a1 += red[w][1]; }
-      q.partials[2 * blockIdx.x] = a0;
-      q.partials[2 * blockIdx.x + 1] = a1;
+    if (threadIdx.x < 4) {
+      double a0 = 0.0;
+      for (int w = 0; w < kWarpsPerBlock; ++w) a0 += red[w][threadIdx.x];
+      q.partials[4 * blockIdx.x + threadIdx.x] = a0;
     }
   }
 }

@@ -175,6 +175,19 @@ class UHandle:
                                        int(include_obs_terms), _ptr(out)))
         return float(out[0]), float(out[1]), int(out[2])
 
+    def loglik_z(self, covType, covparms, nuggets, nuggets_obsord, zord, include_obs_terms=-1):
+        """Whole log-likelihood for pure `z` conditioning (gpv_loglik_z): dict(loglik, quadform_num,
+        logdet_num, quadform_denom, logdet_denom, nfail)."""
+        cov = _f64(covparms)
+        nug = _f64(nuggets)
+        tau = _f64(nuggets_obsord)
+        z = _f64(zord)
+        out = np.zeros(6, dtype=np.float64)
+        check(lib.gpv_loglik_z(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau), _ptr(z),
+                               tau.size, int(include_obs_terms), _ptr(out)))
+        return dict(loglik=float(out[0]), quadform_num=float(out[1]), logdet_num=float(out[2]),
+                    quadform_denom=float(out[3]), logdet_denom=float(out[4]), nfail=int(out[5]))
+
     def u_dev(self, covType, covparms, d_nuggets, d_out=None, packed=False, d_zord=None, skip_rows=0,
               d_loglik=None, stream=None):
         """Device-pointer variant (ints are raw device addresses, e.g. torch_tensor.data_ptr())."""
@@ -424,6 +437,14 @@ def vecchia_likelihood_U(z, U_obj):
 
 
 def vecchia_likelihood(z, vecchia_approx, covparms, nuggets, covmodel="matern", device=0):
+    va = vecchia_approx
+    if va["cond_yz"] == "z" and bool(np.all(va["obs"])) and isinstance(covmodel, str) \
+            and not np.any(np.asarray(nuggets) == 0):
+        # standard Vecchia: numerator and denominator are per-row closed forms, all on the GPU
+        n, size, latent, ord_, obs, nug, nuggets_all_ord, nuggets_ord = _prepare_nuggets(va, nuggets)
+        h = _handle_for(va, device)
+        zord = np.asarray(z, dtype=np.float64)[np.asarray(va["ord_z"]) - 1]
+        return h.loglik_z(covmodel, covparms, nuggets_all_ord, nuggets_ord, zord)["loglik"]
     if vecchia_approx["cond_yz"] == "zy":
         import warnings
         warnings.warn("cond.yz='zy' will produce a poor likelihood approximation. Use 'SGV' instead.")

@@ -106,10 +106,23 @@ gpv_status gpv_loglik_numerator(gpv_handle* h, const char* covType, const double
                                 const double* zord, int64_t n, int64_t skip_rows,
                                 int include_obs_terms, double out[3]);
 
+/* ---- whole log-likelihood on the GPU for standard Vecchia (`cond.yz = "z"`, every location observed)
+ * With pure `z` conditioning U_y U_y^T is diagonal, so the denominator of vecchia_likelihood_U
+ * (R/vecchia_likelihood.R:85-91: U2V, sparse Cholesky, triangular solve) reduces to per-row closed
+ * forms W_kk = x_kk^2 + 1/tau_k and z2_k = x_kk q_k - z_k/tau_k, accumulated by the same fused kernel.
+ * out[0] = log-likelihood (:95-96; meaningful when the handle holds every row), out[1] = quadform.num,
+ * out[2] = logdet.num, out[3] = quadform.denom, out[4] = logdet.denom, out[5] = failed rows; parts
+ * 1..4 are restricted to the handle's row shard (sum them over ranks).  GPV_ERR_UNSUPPORTED for any
+ * other layout (SGV, y, zy, prediction): use gpv_loglik_numerator + the reference's denominator. */
+gpv_status gpv_loglik_z(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
+                        const double* nuggets, const double* nuggets_obsord, const double* zord,
+                        int64_t n, int include_obs_terms, double out[6]);
+
 /* ---- device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`) ------
  * d_nuggets[Nlocs] device pointer.  d_out: row-major (rows x p) when packed == 0, packed order
  * otherwise.  stream: a cudaStream_t cast to void* (NULL = the handle's own stream).
- * d_loglik (may be NULL): 3 doubles {quadform rows part, logdet rows part, nfail}; requires
+ * d_loglik (may be NULL): 5 doubles {quadform.num rows part, logdet.num rows part, nfail,
+ * quadform.denom, logdet.denom (pure `z` layouts only, else 0)}; requires
  * d_zord (n doubles, device) and obs at create time.  d_out may be NULL when only the
  * likelihood is wanted. */
 gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,

@@ -438,3 +438,54 @@ def test_chunked_packed_pipeline_matches_single_launch(layout):
         ref = pr.Lentries()
         scale = np.abs(ref).max(axis=1, keepdims=True)
         assert (np.abs(r["Lentries"][a:b] - ref) / scale).max() < 1e-9
+
+
+def test_whole_loglik_on_gpu_for_pure_z_conditioning():
+    # standard Vecchia: denominator terms are per-row closed forms (gpv_loglik_z)
+    n, m = 3000, 20
+    va = _problem(n, m, 2, "z", stream=98)
+    prep = va["U_prep"]
+    z = H.make_data(n, stream=98)
+    tau = H.make_nuggets(n, stream=98)
+    for covType, cp in (("matern", [1.2, 0.06, 1.5]), ("matern", [0.9, 0.05, 0.8]), ("esqe", [0.7, 0.05, 0.4, 0.03])):
+        with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+            r = h.loglik_z(covType, cp, tau, tau, z)
+        Uo = O.createU(va, cp, tau, covmodel=covType)
+        ll_ref = O.vecchia_likelihood_U(z, Uo)
+        qr, lr, _ = O.loglik_numerator_from_U(z, Uo)
+        assert r["nfail"] == 0
+        assert abs(r["quadform_num"] - qr) <= LL_TOL * abs(qr) and abs(r["logdet_num"] - lr) <= LL_TOL * abs(lr)
+        assert abs(r["loglik"] - ll_ref) <= LL_TOL * abs(ll_ref), (covType, r["loglik"], ll_ref)
+        assert abs(G.vecchia_likelihood(z, va, cp, tau, covmodel=covType) - ll_ref) <= LL_TOL * abs(ll_ref)
+    # known answer: m = n-1 => exact Gaussian log-density
+    n2 = 31
+    locs = H.make_locs(n2, 2, stream=99)
+    NN = H.ordered_nn_kdtree(locs, n2 - 1)
+    va2 = H.make_vecchia_approx(locs, NN, H.layout_yz(NN, "z"), np.ones(n2, dtype=bool), "z")
+    z2 = H.make_data(n2, stream=99)
+    ll = G.vecchia_likelihood(z2, va2, [1.3, 0.25, 2.5], 0.2)
+    ex = O.exact_loglik(z2, locs, [1.3, 0.25, 2.5], 0.2)
+    assert abs(ll - ex) <= LL_TOL * abs(ex)
+    # shards: parts add up
+    cp = [1.2, 0.06, 1.5]
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+        whole = h.loglik_z("matern", cp, tau, tau, z)
+    acc = dict(quadform_num=0.0, logdet_num=0.0, quadform_denom=0.0, logdet_denom=0.0)
+    for a, b in ((0, 1100), (1100, 3000)):
+        with G.UHandle(va["locsord"], prep["revNNarray"][a:b], prep["revCond"][a:b], obs=va["obs"],
+                       row_begin=a, row_end=b) as hs:
+            part = hs.loglik_z("matern", cp, tau, tau, z)
+            for k in acc:
+                acc[k] += part[k]
+    for k in acc:
+        assert abs(acc[k] - whole[k]) <= 1e-11 * abs(whole[k]), k
+
+
+def test_loglik_z_refuses_other_layouts():
+    va = _problem(400, 6, 2, "SGV", stream=100)
+    prep = va["U_prep"]
+    tau = np.full(400, 0.1)
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+        with pytest.raises(G.GpvError) as ei:
+            h.loglik_z("matern", [1.0, 0.1, 1.5], tau, tau, np.zeros(400))
+        assert ei.value.status == 5
