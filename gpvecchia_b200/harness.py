@@ -140,6 +140,47 @@ def layout_zy(locsord, m, n):
     return np.vstack([locs, locs]), NNarray, Cond, obs
 
 
+def layout_zy_pred(locs_obs, locs_pred, m, device=0, use_gpu=True):
+    """Response-first 'zy' layout WITH prediction locations in obs-then-pred ordering
+    (vecchia_specify.R:120-149,191-224; BASELINE configs[4]): returns (locsord, NNarray, Cond, obs)
+    with N = 2 n + n_pred rows (n dummy z rows with n0 = 1, then n + n_pred full rows).
+    The ordered search for the prediction rows runs on the GPU harness, the unordered k-NN among the
+    observations (FNN::get.knn) on a cKDTree."""
+    from scipy.spatial import cKDTree
+    locs_obs = np.asarray(locs_obs, dtype=np.float64)
+    locs_pred = np.asarray(locs_pred, dtype=np.float64)
+    n, n_p = locs_obs.shape[0], locs_pred.shape[0]
+    locs_all = np.vstack([locs_obs, locs_pred])
+    # ordered NN of the prediction rows among everything before them (:159)
+    if use_gpu:
+        rev = ordered_nn_gpu(locs_all, m, n, n + n_p, device=device).astype(np.int64)
+        NN_pred = rev[:, ::-1]
+    else:
+        NN_pred = ordered_nn_kdtree(locs_all, m, n, n + n_p)
+    tree = cKDTree(locs_obs)
+    _, idx = tree.query(locs_obs, k=m, workers=-1)
+    own = np.arange(n)[:, None]
+    notself = idx != own
+    # drop self (normally column 0); rows where self is missing from the k results are impossible
+    # without exact duplicates, keep the first m-1 others
+    order = np.argsort(~notself, axis=1, kind="stable")
+    NNs = np.take_along_axis(idx, order, axis=1)[:, :m - 1].astype(np.int64) + 1
+    prev = NNs < (own + 1)
+    NNs[prev] += n
+    NNarray_z = np.zeros((n, m + 1), dtype=np.int64)
+    NNarray_z[:, 0] = np.arange(1, n + 1)
+    NNarray_y = np.concatenate([own + 1 + n, own + 1, NNs], axis=1)
+    NNarray_yp = NN_pred.copy()
+    NNarray_yp[NNarray_yp != 0] += n
+    NNarray = np.vstack([NNarray_z, NNarray_y, NNarray_yp])
+    Cond = -np.ones(NNarray.shape, dtype=np.int8)
+    nz = NNarray != 0
+    Cond[nz] = (NNarray[nz] > n).astype(np.int8)
+    Cond[:, 0] = 1
+    obs = np.concatenate([np.ones(n, dtype=bool), np.zeros(n + n_p, dtype=bool)])
+    return np.vstack([locs_obs, locs_all]), NNarray, Cond, obs
+
+
 def make_vecchia_approx(locsord, NNarray, Cond, obs, cond_yz, ord_=None, ord_z=None,
                         ord_pred="general", U_sparsity=None):
     """Assemble the vecchia.approx list (vecchia_specify.R:234-236) from harness-made inputs."""

@@ -68,3 +68,12 @@ def test_row_sharding_partitions_full_rows_evenly():
         loads = [w[cuts[r]:cuts[r + 1]].sum() for r in range(world)]
         assert max(loads) <= 1.02 * (w.sum() / world) + 31 ** 3
     assert shard.row_cuts(np.full(10, 5), 4).tolist() == [0, 3, 5, 8, 10]
+
+
+def test_layout_zy_pred_matches_specify_restatement():
+    locs = H.make_locs(250, 2, stream=6)
+    lp = H.make_locs(60, 2, stream=7)
+    va = O.vecchia_specify(locs, 8, cond_yz="zy", locs_pred=lp)
+    locs2, NN, Cond, obs = H.layout_zy_pred(locs, lp, 8, use_gpu=False)
+    assert np.array_equal(NN, va["NNarray"]) and np.array_equal(Cond, va["Cond"])
+    assert np.array_equal(obs, va["obs"]) and np.array_equal(locs2, va["locsord"])
