@@ -103,6 +103,15 @@ __constant__ double kMathC[24] = {
     0.0, 0.0, 0.0};
 __constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to shared memory per block
 
+#ifndef GPV_MINB21
+#define GPV_MINB21 4
+#endif
+#ifndef GPV_MINB26
+#define GPV_MINB26 4
+#endif
+#ifndef GPV_MINB41
+#define GPV_MINB41 3
+#endif
 #ifndef GPV_MINB32
 #define GPV_MINB32 4
 #endif
@@ -383,7 +392,10 @@ __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict_
 
 // resident blocks per SM the register allocation is sized for (shared memory allows the same)
 template <int P>
-struct Occupancy { static constexpr int kMinBlocks = (P <= 16) ? 4 : (P <= 32) ? GPV_MINB32 : (P <= 41) ? 2 : 1; };
+struct Occupancy {
+  static constexpr int kMinBlocks = (P <= 21) ? GPV_MINB21 : (P <= 26) ? GPV_MINB26 : (P <= 32) ? GPV_MINB32
+                                    : (P <= 41) ? GPV_MINB41 : 1;
+};
 
 // GENERAL = false: the closed forms (exp, Matern 1.5 / 2.5, esqe) selected at run time by q.cov;
 // GENERAL = true : the general-nu table path.  Separate instantiations so that the general path's
