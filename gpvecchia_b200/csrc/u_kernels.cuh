@@ -249,8 +249,8 @@ struct SetLayout {
   static constexpr int DD = (D > 0) ? D : GPV_MAX_D;
   static constexpr int NLOW = (P + 1) / 2;                 // rows 0..NLOW-1, row q on lane q
   static constexpr int NHIGH = P / 2;                      // rows P-1..NLOW, row P-1-q on lane q
-  static constexpr int kScratch = tri_col(P, P);           // dump slot for inactive pair stores
-  static constexpr int kBuf = ((tri_col(P, P) + 2) / 2) * 2;
+  static constexpr int kScratch = tri_col(P, P);           // per-lane dump slots for inactive pair stores
+  static constexpr int kBuf = ((tri_col(P, P) + G + 1) / 2) * 2;
   static constexpr int kT = P / 2;                         // pair-stage iterations
   static constexpr int PX = ((P + 1) / 2) * 2;             // coordinate row stride
   static constexpr int kX = DD * PX;                       // coordinates of the P points
@@ -314,7 +314,7 @@ __device__ __forceinline__ void build_store_table(unsigned* __restrict__ stab) {
   for (int idx = threadIdx.x; idx < LY::kT * G; idx += blockDim.x) {
     const int t = idx / G + 1, q = idx % G;
     const bool full = (2 * t < P);                       // even P: t = P/2 is covered by i < P/2 only
-    unsigned lo16 = LY::kScratch, hi16 = LY::kScratch;
+    unsigned lo16 = LY::kScratch + q, hi16 = LY::kScratch + q;   // own dump slot: no write-write race
     if (q < LY::NLOW && (full || q < P / 2)) {
       const int i = q;
       int j = i + t; if (j >= P) j -= P;

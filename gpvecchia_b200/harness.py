@@ -86,6 +86,8 @@ def ordered_nn_gpu(locs, m, row_begin=0, row_end=None, device=0):
     library's GPU grid search (gpv_harness_ordered_nn)."""
     locs = np.asarray(locs, dtype=np.float64)
     N, d = locs.shape
+    if d > 3 or m > 63:
+        raise ValueError("gpv_harness_ordered_nn supports d <= 3 and m <= 63; use ordered_nn_kdtree")
     row_end = N if row_end is None else row_end
     nrows = row_end - row_begin
     out = np.zeros((m + 1) * nrows, dtype=np.int32)

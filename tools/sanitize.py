@@ -1,0 +1,30 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import gpvecchia_b200 as G
+from gpvecchia_b200 import harness as H
+
+for (n, m, d, layout) in ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"), (500, 9, 2, "zy"), (200, 5, 5, "z")):
+    locs = H.make_locs(n, d, stream=1)
+    if layout == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        nug_all = np.concatenate([np.full(n, 0.1), np.zeros(n)])
+    else:
+        NN = (H.rev(H.ordered_nn_gpu(locs, m)) if d <= 3 else H.ordered_nn_kdtree(locs, m)).astype(np.int64)
+        locs2 = locs
+        Cond, obs = H.layout_yz(NN, "z"), np.ones(n, dtype=bool)
+        nug_all = np.full(n, 0.1)
+    tau = nug_all[:n]
+    z = H.make_data(n, stream=1)
+    with G.UHandle(locs2, H.rev(NN), H.rev(Cond), obs=obs) as h:
+        for ct, cp in (("matern", [1.0, 0.2, 1.5]), ("matern", [1.0, 0.2, 0.5]), ("matern", [1.0, 0.2, 2.5]),
+                       ("matern", [1.0, 0.2, 0.8]), ("esqe", [0.7, 0.2, 0.4, 0.1])):
+            h.U_NZentries(ct, cp, nug_all, tau)
+            h.values_packed(ct, cp, nug_all, tau)
+            h.loglik_numerator(ct, cp, nug_all, tau, z, skip_rows=n if layout == "zy" else 0)
+        if layout == "z":
+            h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all, tau, z)
+G.MaternFun(np.linspace(0, 3, 100), [1.0, 0.3, 1.3])
+G.EsqeFun(np.linspace(0, 3, 100), [1.0, 0.3, 0.5, 0.2])
+print("sanitize workload done")
