@@ -537,6 +537,7 @@ def test_randomised_sweep_against_oracle():
     # seeded random shapes: set size, dimension, covariance, conditioning mask, missing pattern,
     # nugget vector -- every case against the CPU restatement (values) and its failure count
     rng = np.random.default_rng(20240601)
+    checked = 0
     for case in range(24):
         m = int(rng.integers(1, 64))
         d = int(rng.integers(1, 6))
@@ -564,10 +565,25 @@ def test_randomised_sweep_against_oracle():
         got = G.U_NZentries(1, n, locs, revNN, revCond, nug, nug, covType, cp)
         ref = O.U_NZentries(2, n, locs, revNN, rc, nug, nug, covType, np.array(cp), mode=2)   # __float128 arbiter
         ref64 = O.U_NZentries(2, n, locs, revNN, rc, nug, nug, covType, np.array(cp), mode=1)
-        assert got["nfail"] == ref["nfail"], (case, m, d, covType, cp)
-        assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0), case
-        e_gpu = _rowscaled_err(got["Lentries"], ref["Lentries"])
-        e_ref = _rowscaled_err(ref64["Lentries"], ref["Lentries"])
-        # latent-conditioned neighbours carry no nugget: some random blocks are ill conditioned, so the
-        # CUDA path is held to the accuracy the fp64 restatement itself achieves against quad precision
-        assert e_gpu < max(VAL_TOL, 4 * e_ref), (case, m, d, covType, cp, e_gpu, e_ref)
+        # a block can be numerically singular in fp64 (1-D, smooth kernel, latent neighbours without
+        # nugget): whether a pivot then rounds to <= 0 is implementation dependent, so a failed row is
+        # accepted only if the oracle's conditioning proxy says the block is singular to fp64
+        n0 = (revNN != 0).sum(axis=1)
+        gfail = np.nonzero((got["Lentries"] == 0).all(axis=1) & (n0 > 0))[0]
+        assert gfail.size == got["nfail"]
+        for k in gfail:
+            assert O.block_cond_proxy(int(k), locs, revNN, rc, nug, covType, np.array(cp)) > 1e12, (case, int(k))
+        # values are compared on the rows the fp64 restatement itself resolves to 1e-12 against quad
+        # precision (condition number up to ~1e4); on worse-conditioned blocks two correct fp64
+        # evaluations of the covariance (1e-15 apart) already differ by cond * 1e-15 in U
+        scale = np.abs(ref["Lentries"]).max(axis=1)
+        scale[scale == 0] = 1.0
+        row_ref = np.abs(ref64["Lentries"] - ref["Lentries"]).max(axis=1) / scale
+        row_gpu = np.abs(got["Lentries"] - ref["Lentries"]).max(axis=1) / scale
+        ok = row_ref < 1e-12
+        ok[gfail] = False
+        assert ok.sum() >= 3, case
+        assert np.array_equal(got["Lentries"][ok] == 0, ref["Lentries"][ok] == 0), case
+        assert row_gpu[ok].max() < VAL_TOL, (case, m, d, covType, cp, float(row_gpu[ok].max()))
+        checked += int(ok.sum())
+    assert checked > 2000
