@@ -4,9 +4,9 @@ hot path behind the reference's own interface.  The CUDA C-ABI library
 the host-side mirror of the reference's R interface for that path.  Importing fails loudly when
 the library has not been built: there is no CPU fallback."""
 from ._lib import lib, GpvError, LIB_PATH
-from .host import (UHandle, U_NZentries, MaternFun, EsqeFun, U_sparsity, createU,
+from .host import (UHandle, MultiHandle, U_NZentries, MaternFun, EsqeFun, U_sparsity, createU,
                    vecchia_likelihood, vecchia_likelihood_U, vecchia_loglik_numerator)
 
-__all__ = ["lib", "GpvError", "LIB_PATH", "UHandle", "U_NZentries", "MaternFun", "EsqeFun",
+__all__ = ["lib", "GpvError", "LIB_PATH", "UHandle", "MultiHandle", "U_NZentries", "MaternFun", "EsqeFun",
            "U_sparsity", "createU", "vecchia_likelihood", "vecchia_likelihood_U",
            "vecchia_loglik_numerator"]

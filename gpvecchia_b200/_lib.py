@@ -21,6 +21,9 @@ EXPORTED = [
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
+    "gpv_multi_create", "gpv_multi_destroy", "gpv_multi_num_devices", "gpv_multi_packed_len",
+    "gpv_multi_row_cuts", "gpv_multi_set_revcond", "gpv_multi_u_values_packed",
+    "gpv_multi_loglik_numerator", "gpv_multi_loglik_z", "gpv_set_last_error",
 ]
 
 
@@ -82,6 +85,26 @@ def _load():
     L.gpv_measure_copy_bw.restype = i32
     L.gpv_harness_ordered_nn.argtypes = [i64, i32, i32, vp, i64, i64, vp, i32]
     L.gpv_harness_ordered_nn.restype = i32
+    L.gpv_multi_create.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, vp, i32]
+    L.gpv_multi_create.restype = i32
+    L.gpv_multi_destroy.argtypes = [vp]
+    L.gpv_multi_destroy.restype = None
+    L.gpv_multi_num_devices.argtypes = [vp]
+    L.gpv_multi_num_devices.restype = i32
+    L.gpv_multi_packed_len.argtypes = [vp]
+    L.gpv_multi_packed_len.restype = i64
+    L.gpv_multi_row_cuts.argtypes = [vp, vp]
+    L.gpv_multi_row_cuts.restype = None
+    L.gpv_multi_set_revcond.argtypes = [vp, vp, i32]
+    L.gpv_multi_set_revcond.restype = i32
+    L.gpv_multi_u_values_packed.argtypes = [vp, cp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_multi_u_values_packed.restype = i32
+    L.gpv_multi_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, vp]
+    L.gpv_multi_loglik_numerator.restype = i32
+    L.gpv_multi_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, vp]
+    L.gpv_multi_loglik_z.restype = i32
+    L.gpv_set_last_error.argtypes = [cp]
+    L.gpv_set_last_error.restype = None
     # host-only self-test hooks of the general-nu machinery (single points; not a compute path)
     L.gpv_selftest_matern_general_host.argtypes = [dbl, dbl, dbl]
     L.gpv_selftest_matern_general_host.restype = dbl

@@ -47,6 +47,7 @@ static gpv_status fail(gpv_status st, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* gpv_last_error(void) { return g_err; }
+extern "C" void gpv_set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
 extern "C" const char* gpv_version(void) { return "gpvecchia_b200 0.1 (sm_100a)"; }
 extern "C" int gpv_device_count(void) {
   int n = 0;

@@ -214,6 +214,77 @@ class UHandle:
         return lib.gpv_last_kernel_name(self._h).decode()
 
 
+class MultiHandle:
+    """One process, several GPUs (gpv_multi_*): what an R session would hold.  Rows are split into
+    contiguous ranges balancing sum n0^3; every device writes its slice of the packed vector."""
+
+    def __init__(self, locsord, revNNarray, revCond, obs=None, devices=(0,)):
+        locs = np.asarray(locsord, dtype=np.float64)
+        self.N, self.d = locs.shape
+        nn = _nn_to_i32(revNNarray)
+        self.p = nn.shape[1]
+        obs_i32 = None
+        self.n_obs = 0
+        if obs is not None:
+            obs_i32 = np.ascontiguousarray(np.asarray(obs).astype(bool).astype(np.int32))
+            self.n_obs = int(obs_i32.sum())
+        dev = np.ascontiguousarray(np.asarray(devices, dtype=np.int32))
+        h = C.c_void_p()
+        check(lib.gpv_multi_create(C.byref(h), self.N, self.p, self.d, _ptr(_colmajor(locs, np.float64)),
+                                   _ptr(_colmajor(nn, np.int32)),
+                                   _ptr(_colmajor(_cond_to_rlogical(revCond), np.int32)),
+                                   _lib.GPV_COND_RLOGICAL_I32, _ptr(obs_i32), _ptr(dev), dev.size))
+        self._h = h
+        self.packed_len = int(lib.gpv_multi_packed_len(h))
+        cuts = np.zeros(dev.size + 1, dtype=np.int64)
+        lib.gpv_multi_row_cuts(h, _ptr(cuts))
+        self.row_cuts = cuts
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.gpv_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def values_packed(self, covType, covparms, nuggets, nuggets_obsord, zentries_tail=True, out=None):
+        cov, nug, tau = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord)
+        n = tau.size
+        total = self.packed_len + (2 * n if zentries_tail else 0)
+        if out is None:
+            out = np.empty(total, dtype=np.float64)
+        nfail, first = C.c_int64(0), C.c_int64(-1)
+        check(lib.gpv_multi_u_values_packed(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug),
+                                            _ptr(tau), n, 1 if zentries_tail else 0, _ptr(out),
+                                            C.byref(nfail), C.byref(first)))
+        return out, int(nfail.value), int(first.value)
+
+    def loglik_numerator(self, covType, covparms, nuggets, nuggets_obsord, zord, skip_rows=0):
+        cov, nug, tau, z = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord), _f64(zord)
+        out = np.zeros(3, dtype=np.float64)
+        check(lib.gpv_multi_loglik_numerator(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug),
+                                             _ptr(tau), _ptr(z), tau.size, int(skip_rows), _ptr(out)))
+        return float(out[0]), float(out[1]), int(out[2])
+
+    def loglik_z(self, covType, covparms, nuggets, nuggets_obsord, zord):
+        cov, nug, tau, z = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord), _f64(zord)
+        out = np.zeros(6, dtype=np.float64)
+        check(lib.gpv_multi_loglik_z(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau),
+                                     _ptr(z), tau.size, _ptr(out)))
+        return dict(loglik=float(out[0]), quadform_num=float(out[1]), logdet_num=float(out[2]),
+                    quadform_denom=float(out[3]), logdet_denom=float(out[4]), nfail=int(out[5]))
+
+
 # --------------------------------------------------------------------------------------------------
 # the reference's stateless entry points
 # --------------------------------------------------------------------------------------------------

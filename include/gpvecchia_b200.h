@@ -140,6 +140,34 @@ const char* gpv_last_kernel_name(const gpv_handle* h);
 /* Number of kernels this library launched since load (monotone counter; bench's gpu_launches). */
 int64_t gpv_launch_count(void);
 
+/* ---- one process, several GPUs (the form an R session uses) -------------------------------------
+ * One handle per device, driven by worker threads inside the library.  Rows are split into
+ * contiguous ranges balancing sum n0^3; each device writes its slice of the packed vector directly
+ * into `out`; likelihood partial sums are added on the host in device order.  There is no
+ * inter-GPU data path (rows are independent), so no collective is involved.  `devices` may repeat
+ * an ordinal (several shards on one GPU). */
+typedef struct gpv_multi gpv_multi;
+gpv_status gpv_multi_create(gpv_multi** out, int64_t Nlocs, int p, int d, const double* locs,
+                            const int32_t* revNNarray, const void* revCondOnLatent,
+                            gpv_cond_type cond_type, const int32_t* obs, const int* devices, int ndev);
+void gpv_multi_destroy(gpv_multi* m);
+int gpv_multi_num_devices(const gpv_multi* m);
+int64_t gpv_multi_packed_len(const gpv_multi* m);
+void gpv_multi_row_cuts(const gpv_multi* m, int64_t* cuts /* ndev + 1 */);
+gpv_status gpv_multi_set_revcond(gpv_multi* m, const void* revCondOnLatent, gpv_cond_type cond_type);
+gpv_status gpv_multi_u_values_packed(gpv_multi* m, const char* covType, const double* covparms,
+                                     int ncovparms, const double* nuggets, const double* nuggets_obsord,
+                                     int64_t n, int zentries_tail, double* out, int64_t* nfail,
+                                     int64_t* first_fail);
+gpv_status gpv_multi_loglik_numerator(gpv_multi* m, const char* covType, const double* covparms,
+                                      int ncovparms, const double* nuggets, const double* nuggets_obsord,
+                                      const double* zord, int64_t n, int64_t skip_rows, double out[3]);
+gpv_status gpv_multi_loglik_z(gpv_multi* m, const char* covType, const double* covparms, int ncovparms,
+                              const double* nuggets, const double* nuggets_obsord, const double* zord,
+                              int64_t n, double out[6]);
+/* sets the calling thread's gpv_last_error() text (used by the multi-GPU front end) */
+void gpv_set_last_error(const char* msg);
+
 /* ---- stateless drop-in: the reference's nine arguments, everything uploaded per call ---------
  * Mirrors U_NZentries(Ncores, n, locs, revNNarray, revCondOnLatent, nuggets, nuggets_obsord,
  * covType, covparms) (src/U_NZentries.cpp:25); Ncores is accepted and ignored. */

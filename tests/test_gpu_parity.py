@@ -587,3 +587,40 @@ def test_randomised_sweep_against_oracle():
         assert row_gpu[ok].max() < VAL_TOL, (case, m, d, covType, cp, float(row_gpu[ok].max()))
         checked += int(ok.sum())
     assert checked > 2000
+
+
+@pytest.mark.parametrize("layout", ["z", "zy"])
+def test_single_process_multi_device_front_end(layout):
+    # gpv_multi_*: worker threads, one shard per entry of `devices` (an ordinal may repeat, so the
+    # slicing logic is exercised on a one-GPU box; on an N-GPU box pass range(N))
+    n, m = 5000, 12
+    locs = H.make_locs(n, 2, stream=101)
+    if layout == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        nug_all = np.concatenate([H.make_nuggets(n, stream=101), np.zeros(n)])
+    else:
+        locs2, NN = locs, H.ordered_nn_kdtree(locs, m)
+        Cond, obs = H.layout_yz(NN, "z"), np.ones(n, dtype=bool)
+        nug_all = H.make_nuggets(n, stream=101)
+    revNN, revCond = H.rev(NN), H.rev(Cond)
+    tau, z = nug_all[:n], H.make_data(n, stream=101)
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    skip = n if layout == "zy" else 0
+    with G.UHandle(locs2, revNN, revCond, obs=obs) as h:
+        want, nf, _ = h.values_packed("matern", cp, nug_all, tau)
+        q, l, _ = h.loglik_numerator("matern", cp, nug_all, tau, z, skip_rows=skip)
+        llz = h.loglik_z("matern", cp, nug_all, tau, z) if layout == "z" else None
+    ndev = G.lib.gpv_device_count()
+    for devices in ([0], [0, 0, 0], list(range(ndev)) * 2):
+        with G.MultiHandle(locs2, revNN, revCond, obs=obs, devices=devices) as mh:
+            assert mh.row_cuts[0] == 0 and mh.row_cuts[-1] == locs2.shape[0] and mh.packed_len == want.size - 2 * n
+            got, nf2, _ = mh.values_packed("matern", cp, nug_all, tau)
+            assert nf2 == nf and np.array_equal(got, want)
+            q2, l2, _ = mh.loglik_numerator("matern", cp, nug_all, tau, z, skip_rows=skip)
+            assert abs(q2 - q) <= 1e-12 * abs(q) and abs(l2 - l) <= 1e-12 * abs(l)
+            if layout == "z":
+                r = mh.loglik_z("matern", cp, nug_all, tau, z)
+                assert abs(r["loglik"] - llz["loglik"]) <= 1e-12 * abs(llz["loglik"])
+            if layout == "zy" and len(devices) == 3:
+                # the n dummy rows are free: the first cut lies beyond them
+                assert mh.row_cuts[1] > n
