@@ -86,21 +86,12 @@ constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
 // Polynomial / reduction constants live in constant memory so DFMA takes them as c[bank][offset]
 // operands; as literals ptxas re-materialised them with two UMOVs each inside the pair loop
 // (8% of all issued instructions in the first profile, profiles/r01_*).
-#ifndef GPV_EXP_TABLE
-#define GPV_EXP_TABLE 1
-#endif
-__constant__ double kMathC[24] = {
+__constant__ double kMathC[8] = {
     GPV_EXP_Q0, GPV_EXP_Q1, GPV_EXP_Q2, GPV_EXP_Q3,
     GPV_EXP_64_OVER_LN2,           // [4]
     -GPV_EXP_LN2_64_HI,            // [5]
     -GPV_EXP_LN2_64_LO,            // [6]
-    1.0e-300,                      // [7] sqrt guard
-    GPV_EXP_C2, GPV_EXP_C3, GPV_EXP_C4, GPV_EXP_C5, GPV_EXP_C6, GPV_EXP_C7, GPV_EXP_C8, GPV_EXP_C9,
-    GPV_EXP_C10, GPV_EXP_C11,      // [8..17] no-table polynomial
-    1.4426950408889634,            // [18] log2(e)
-    -6.93147180369123816490e-01,   // [19] -ln2 hi
-    -1.90821492927058770002e-10,   // [20] -ln2 lo
-    0.0, 0.0, 0.0};
+    1.0e-300};                     // [7] sqrt guard
 __constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to shared memory per block
 
 #ifndef GPV_MINB21
@@ -114,15 +105,6 @@ __constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to s
 #endif
 #ifndef GPV_MINB32
 #define GPV_MINB32 4
-#endif
-#ifndef GPV_EXP_ESTRIN
-#define GPV_EXP_ESTRIN 0
-#endif
-#ifndef GPV_RSQRT_NEWTON
-#define GPV_RSQRT_NEWTON 0
-#endif
-#ifndef GPV_PAIR_UNROLL
-#define GPV_PAIR_UNROLL 1
 #endif
 
 __device__ __forceinline__ double rsqrt_seed(double a) {
@@ -148,18 +130,13 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
 // NaN (Inf * 0 from a latent-conditioned Inf nugget, U_NZentries.cpp:47) passes through and fails
 // the row like dpotrf does.
 __device__ __forceinline__ double clamp_nugget(double v) { return (v > 1.0e300) ? 1.0e300 : v; }
-// 1/a for finite normal a > 0 to ~1 ulp (cubic step from the MUFU.RCP64H seed, + optional Newton
-// step); a <= 0 / NaN / Inf: garbage, callers test `a > 0` themselves.
+// 1/a for finite normal a > 0 to ~1 ulp: one cubic step from the MUFU.RCP64H seed (measured seed
+// error 2^-19.9, tools/microbench/lat.cu); a <= 0 / NaN / Inf: garbage, callers test the pivot.
 __device__ __forceinline__ double rcp_pos(double a) {
   double y0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
   const double e = fma(-a, y0, 1.0);
-  double y = fma(fma(e, e, e), y0, y0);                      // y0 (1 + e + e^2): error ~ e^3
-#if GPV_RSQRT_NEWTON
-  const double e1 = fma(-a, y, 1.0);
-  y = fma(y, e1, y);
-#endif
-  return y;
+  return fma(fma(e, e, e), y0, y0);                          // y0 (1 + e + e^2): error ~ e^3 = 2^-60
 }
 // sqrt(w) for w > 0 to ~1 ulp: cubic rsqrt + one Goldschmidt correction, no select.  Callers add
 // kSqrtGuard = 1e-300 to the squared distance (fused into its last FMA), which keeps w == 0
@@ -182,20 +159,6 @@ __device__ __forceinline__ double sqrt_pos(double w) {
 __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ etab) {
   s = (s > 700.0) ? 700.0 : s;                               // NaN stays NaN
   const double kShift = 6755399441055744.0;                  // 1.5 * 2^52
-#if !GPV_EXP_TABLE
-  {
-    const double t = fma(-s, kMathC[18], kShift);            // round(-s / ln2)
-    const double kf = t - kShift;
-    double r = fma(kf, kMathC[19], -s);
-    r = fma(kf, kMathC[20], r);
-    double p = kMathC[17];
-#pragma unroll
-    for (int i = 16; i >= 8; --i) p = fma(p, r, kMathC[i]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + __double2loint(t) * 1048576, __double2loint(p));
-  }
-#endif
   const double t = fma(-s, kMathC[4], kShift);               // round(-64 s / ln2) in the low mantissa bits
   const double kf = t - kShift;
   double r = fma(kf, kMathC[5], -s);
@@ -378,16 +341,10 @@ __device__ __forceinline__ void pair_stage(const UParams& q, double* __restrict_
   const int ih = (gl < LY::NHIGH) ? (P - 1 - gl) : (P - 1);
   const unsigned* stab_lane = stab + gl;
   constexpr int T = LY::kT;
-  int t = 1;
-#if GPV_PAIR_UNROLL == 2
+  // kept rolled: two evaluations per lane already give two independent chains, and unrolling by two
+  // measured within 1%
 #pragma unroll 1
-  for (; t + 1 <= T; t += 2) {
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t, d);
-    pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t + 1, d);
-  }
-#endif
-#pragma unroll 1
-  for (; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t, d);
+  for (int t = 1; t <= T; ++t) pair_eval_store<KIND, G, P, D>(q, As, xs, xl, xh, il, ih, stab_lane, etab, t, d);
 }
 
 // resident blocks per SM the register allocation is sized for (shared memory allows the same)
@@ -605,7 +562,7 @@ u_sets_kernel(const UParams q) {
       // positive, normal, finite -- dpotrf's `ajj <= 0 || isnan(ajj)` test on the integer pipe
       fail = fail || ((unsigned)(__double2hiint(akk) - 0x00100000) >= 0x7fe00000u);
       if (k == P - 1) { dlast = akk; break; }
-      const double inv = rcp_pos(akk);      // +Inf -> 0 : an Inf nugget decouples that neighbour
+      const double inv = rcp_pos(akk);      // an Inf nugget arrives here as 1e300 (clamp_nugget)
       // publish L[r][k] = a[r][k] / d_k for r >= k (a packed column must not be written above its top)
       const int ck = tri_col(k, P) - k;     // L[r][k] at buf[ck + r]
       double cl = 0.0;
