@@ -79,6 +79,10 @@ struct UParams {
 
 constexpr int kThreadsPerBlock = 128;
 constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
+#ifndef GPV_SOLVE_BLOCK
+#define GPV_SOLVE_BLOCK 1
+#endif
+constexpr int kSolveBlock = GPV_SOLVE_BLOCK;   // rows per shuffle round of the back substitution
 
 // --------------------------------------------------------------------------------------------
 // branch-free fp64 primitives
@@ -597,17 +601,38 @@ u_sets_kernel(const UParams q) {
     }
 
     // ---- 6. x = L^{-T} e_P / sqrt(d_P)  (solve(R, onevec), U_NZentries.cpp:62): unit-triangular column
-    // sweep, j = P-1..1.  s_r accumulates sum_{j > r} L[j][r] y_j with y_r = -s_r; the unit right-hand
-    // side enters as s_{P-1} = -1 (row P-1 is lane 0's high row and is never updated below).
+    // sweep, j = P-1..1, on t = -y: t_r = -sum_{j > r} L[j][r] t_j, and the unit right-hand side enters as
+    // t_{P-1} = -1 (row P-1 is lane 0's high row and is never updated below).  The sweep is a chain of
+    // shuffle -> FMA latencies, so it runs kSolveBlock rows per round: the partial sums of the block's
+    // rows are shuffled together, every lane finishes the block's small triangle redundantly from
+    // broadcast loads, and then applies the block to its own two rows.  Same operations in the same order
+    // as the row-at-a-time sweep, a quarter of the dependent shuffles.
     double sl = 0.0, sh = (gl == 0) ? -1.0 : 0.0;
     const int cbl = tri_col(rl, P) - rl, cbh = tri_col(rh, P) - rh;
 #pragma unroll
-    for (int j = P - 1; j >= 1; --j) {
-      const double yj = (j >= NLOW) ? __shfl_sync(FULL, -sh, base + (P - 1 - j))
-                                    : __shfl_sync(FULL, -sl, base + j);
-      // L[j][r] sits at buf[tri_col(r) - r + j]
-      if (rl < j) sl = fma(buf[cbl + j], yj, sl);
-      if (j > NLOW && rh < j) sh = fma(buf[cbh + j], yj, sh);
+    for (int j = P - 1; j >= 1; j -= kSolveBlock) {
+      double t[kSolveBlock];
+#pragma unroll
+      for (int b = 0; b < kSolveBlock; ++b) {
+        const int r = j - b;
+        if (r < 1) continue;
+        t[b] = (r >= NLOW) ? __shfl_sync(FULL, sh, base + (P - 1 - r)) : __shfl_sync(FULL, sl, base + r);
+      }
+#pragma unroll
+      for (int b = 1; b < kSolveBlock; ++b) {
+        const int r = j - b;
+        if (r < 1) continue;
+#pragma unroll
+        for (int a = 0; a < b; ++a)            // L[j-a][r] sits at buf[tri_col(r) - r + (j - a)]: broadcast
+          t[b] = fma(-buf[tri_col(r, P) - r + (j - a)], t[a], t[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < kSolveBlock; ++b) {
+        const int r = j - b;
+        if (r < 1) continue;
+        if (rl < r) sl = fma(-buf[cbl + r], t[b], sl);
+        if (r > NLOW && rh < r) sh = fma(-buf[cbh + r], t[b], sh);
+      }
     }
     const double rs = rsqrt_pos(dlast);
     double xlow = -sl * rs;
