@@ -205,6 +205,97 @@ __device__ __forceinline__ double cov_eval(double r2, const UParams& q, const do
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// N covariances at a time, written stage by stage across the N independent chains: the same
+// operations in the same order per chain as cov_eval (bit-identical results), but emitted
+// interleaved.  ptxas keeps four inlined cov_eval bodies largely one after the other, which leaves
+// a warp waiting on its own DFMA latency (profiles: `wait` was the top stall of the quad kernel).
+// The argument of the exponential is carried negated (ns = -s): the clamp then selects on what the
+// two FMAs of the range reduction consume, and no DADD is spent on a negation.
+// --------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void sqrt_pos_n(const double (&w)[N], double (&out)[N]) {
+  double y0[N], t[N], e[N], a[N], b2[N], y1[N], g[N], h[N], r[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y0[i] = rsqrt_seed(w[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = w[i] * y0[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-t[i], y0[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { a[i] = fma(e[i], 0.375, 0.5); b2[i] = e[i] * y0[i]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) y1[i] = fma(a[i], b2[i], y0[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { g[i] = w[i] * y1[i]; h[i] = 0.5 * y1[i]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(-g[i], h[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(g[i], r[i], g[i]);
+}
+// exp(ns) for ns <= 0 (clamped at -700), N at a time; same arithmetic as exp_neg(-ns)
+template <int N>
+__device__ __forceinline__ void exp_negarg_n(const double (&ns_in)[N], double (&out)[N],
+                                             const double* __restrict__ etab) {
+  const double kShift = 6755399441055744.0;
+  double ns[N], t[N], kf[N], r[N], T[N], r2[N], qq[N], p[N], v[N];
+  int n[N];
+  // clamp at -700 on the integer pipe: ns <= -0 or NaN, so the high word read as unsigned grows with
+  // |ns|; min(hi, hi(-700)) leaves a (positive, canonical) NaN alone and turns -Inf into -700
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ns[i] = __hiloint2double((int)min((unsigned)__double2hiint(ns_in[i]), 0xC085E000u), __double2loint(ns_in[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fma(ns[i], kMathC[4], kShift);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { kf[i] = t[i] - kShift; n[i] = __double2loint(t[i]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r[i] = fma(kf[i], kMathC[5], ns[i]); T[i] = etab[n[i] & 63]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(kf[i], kMathC[6], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; qq[i] = fma(kMathC[3], r[i], kMathC[2]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) qq[i] = fma(qq[i], r[i], kMathC[1]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) qq[i] = fma(qq[i], r[i], kMathC[0]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(qq[i], r2[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = fma(T[i], p[i], T[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    out[i] = __hiloint2double(__double2hiint(v[i]) + (n[i] >> 6) * 1048576, __double2loint(v[i]));
+}
+struct CovConsts { double c0, c1, c2, c3, c4; };   // what the closed forms read of UParams, by value
+template <int KIND, int N, class C>
+__device__ __forceinline__ void cov_eval_n(const double (&r2)[N], double (&v)[N], const C& q,
+                                           const double* __restrict__ etab) {
+  static_assert(KIND != COV_GENERAL, "closed forms only");
+  double sq[N], ns[N], e[N];
+  sqrt_pos_n<N>(r2, sq);
+#pragma unroll
+  for (int i = 0; i < N; ++i) ns[i] = sq[i] * (-q.c1);
+  exp_negarg_n<N>(ns, e, etab);
+  if (KIND == COV_EXP) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = q.c0 * e[i];
+  } else if (KIND == COV_M15) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fma(-q.c0, ns[i], q.c0) * e[i];
+  } else if (KIND == COV_M25) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = q.c0 * e[i] * fma(ns[i], fma(ns[i], 1.0 / 3.0, -1.0), 1.0);
+  } else {
+    double ns2[N], e2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) ns2[i] = r2[i] * (-q.c3);
+    exp_negarg_n<N>(ns2, e2, etab);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fma(q.c2, e2[i], q.c4 * e[i]);
+  }
+}
+
 // Packed lower triangle, column-major: column k holds rows k..P-1 at tri_col(k) + (r - k).  Used both
 // for the staged covariance matrix and, column by column, for L (a column of L overwrites the
 // staged column it was computed from, which is dead by then).  496 doubles for P = 31 instead of
