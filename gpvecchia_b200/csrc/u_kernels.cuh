@@ -160,22 +160,13 @@ __device__ __forceinline__ double sqrt_pos(double w) {
 // exp(-s) for s >= 0 (clamped at s = 700: below 1e-304 either way), ~1 ulp, no branches:
 // -s = (64 k + j) ln2/64 + r, |r| <= ln2/128; exp(-s) = 2^k * etab[j] * (1 + p(r)), p of degree 5.
 // etab = 2^(j/64) in shared memory (a 64-entry gather; constant memory would serialise it).
+template <int N>
+__device__ __forceinline__ void exp_negarg_n(const double (&ns_in)[N], double (&out)[N], const double* __restrict__ etab);
 __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ etab) {
-  s = (s > 700.0) ? 700.0 : s;                               // NaN stays NaN
-  const double kShift = 6755399441055744.0;                  // 1.5 * 2^52
-  const double t = fma(-s, kMathC[4], kShift);               // round(-64 s / ln2) in the low mantissa bits
-  const double kf = t - kShift;
-  double r = fma(kf, kMathC[5], -s);
-  r = fma(kf, kMathC[6], r);
-  const int n = __double2loint(t);                           // 64 k + j, k <= 0
-  const double T = etab[n & 63];
-  const double r2 = r * r;
-  double qq = fma(kMathC[3], r, kMathC[2]);
-  qq = fma(qq, r, kMathC[1]);
-  qq = fma(qq, r, kMathC[0]);
-  const double p = fma(qq, r2, r);
-  const double v = fma(T, p, T);
-  return __hiloint2double(__double2hiint(v) + (n >> 6) * 1048576, __double2loint(v));
+  const double ns[1] = {0.0 - s};   // not -s: a NaN must keep the sign bit clear for the integer clamp
+  double e[1];
+  exp_negarg_n<1>(ns, e, etab);
+  return e[0];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -415,8 +406,10 @@ __device__ __forceinline__ void pair_eval_store(const UParams& q, double* __rest
       vh = cov_general_fast(r2h, idxh, q.tab);
     }
   } else {
-    vl = cov_eval<KIND>(r2l, q, etab);
-    vh = cov_eval<KIND>(r2h, q, etab);
+    const double r2v[2] = {r2l, r2h};
+    double vv[2];
+    cov_eval_n<(KIND == COV_GENERAL) ? COV_EXP : KIND, 2>(r2v, vv, q, etab);
+    vl = vv[0]; vh = vv[1];
   }
   As[offs & 0xffffu] = vl;
   As[offs >> 16] = vh;

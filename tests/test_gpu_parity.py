@@ -204,6 +204,30 @@ def test_edge_duplicates_zero_inf_and_negative_nuggets():
     assert np.array_equal(got["Zentries"], ref["Zentries"])
 
 
+@pytest.mark.parametrize("m", [8, 30])
+@pytest.mark.parametrize("cov,cp", [("matern", [1.0, 0.2, 0.5]), ("matern", [1.0, 0.2, 1.5]), ("matern", [1.0, 0.2, 2.5]),
+                                    ("matern", [1.0, 0.2, 0.8]), ("esqe", [0.7, 0.2, 0.3, 0.1])])
+def test_nan_coordinate_fails_exactly_the_rows_that_see_it(m, cov, cp):
+    # a NaN coordinate makes every distance to that point NaN, the covariance NaN (no `dist == 0`
+    # branch catches it) and dpotrf's isnan test fails the block (U_NZentries.cpp:60-66): all rows
+    # whose conditioning set holds the point stay zero, every other row is unaffected.  Guards the
+    # integer clamp inside exp (u_kernels.cuh), which must let a NaN argument through.
+    n = 600
+    locs = H.make_locs(n, 2, stream=53)
+    NN = H.ordered_nn_kdtree(locs, m)
+    locs[37, 1] = np.nan
+    va = H.make_vecchia_approx(locs, NN, H.layout_yz(NN, "z"), np.ones(n, dtype=bool), "z")
+    prep = va["U_prep"]
+    nug = np.full(n, 0.1)
+    got = G.U_NZentries(1, n, va["locsord"], prep["revNNarray"], prep["revCond"], nug, nug, cov, cp)
+    sees = np.any(prep["revNNarray"] == 38, axis=1)
+    assert got["nfail"] == int(sees.sum()) and got["first_fail"] == int(np.nonzero(sees)[0].min())
+    assert np.all(got["Lentries"][sees] == 0)
+    clean = locs.copy(); clean[37, 1] = 0.5
+    ref = O.U_NZentries(2, n, clean, prep["revNNarray"], _rc_double(prep["revCond"]), nug, nug, cov, np.array(cp))
+    assert _rowscaled_err(got["Lentries"][~sees], ref["Lentries"][~sees]) < VAL_TOL
+
+
 def test_zero_nugget_createU_trimming():
     n, m = 300, 6
     va = _problem(n, m, 2, "SGV", stream=51)
