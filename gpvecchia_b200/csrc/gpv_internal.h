@@ -10,13 +10,13 @@ namespace gpv {
 struct KernelEntry {
   int G, P, D;                                 // D = 0: runtime d <= GPV_MAX_D
   bool general;                                // general-nu table kernel vs closed forms
-  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: quad-folded (u_quad.cuh)
+  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: band-folded, three or four rows per lane (u_band.cuh)
   const char* name;
   void (*kernel)(const UParams);
   int smem_bytes;
 };
 
-// Picks the smallest instantiated P >= p for dimension d (the quad-folded family wins a tie unless
+// Picks the smallest instantiated P >= p for dimension d (the band-folded family wins a tie unless
 // GPV_KERNEL_FAMILY=fold is set: development knob for A/B timing); nullptr if none.
 const KernelEntry* select_kernel(int p, int d, bool general);
 
@@ -32,7 +32,10 @@ void register_kernels_P32(KernelEntry* out, int* n);
 void register_kernels_P41(KernelEntry* out, int* n);
 void register_kernels_P51(KernelEntry* out, int* n);
 void register_kernels_P64(KernelEntry* out, int* n);
-void register_kernels_Q31(KernelEntry* out, int* n);
-void register_kernels_Q32(KernelEntry* out, int* n);
+void register_kernels_B8_21(KernelEntry* out, int* n);
+void register_kernels_B8_26(KernelEntry* out, int* n);
+void register_kernels_B8_31(KernelEntry* out, int* n);
+void register_kernels_B8_32(KernelEntry* out, int* n);
+void register_kernels_B16_41(KernelEntry* out, int* n);
 
 }  // namespace gpv
