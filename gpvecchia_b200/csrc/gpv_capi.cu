@@ -398,6 +398,14 @@ struct gpv_handle {
   uint64_t* d_cond = nullptr;         // [nrows]
   int64_t* d_row_off = nullptr;       // [nrows]
   int32_t* d_obsrank = nullptr;       // [Nlocs]
+  int32_t* d_obs_excl = nullptr;      // [Nlocs] observations before each location (latent_map[i] = i + excl[i])
+  // compressed-column output (gpv_csc.inc), built on first use
+  bool csc_ready = false;
+  bool cond_uploaded = false;         // the create-time revCond is on the device
+  uint8_t* d_csc_rank = nullptr;      // [nrows][p] place of each compacted entry inside its column
+  uint64_t* d_csc_cond = nullptr;     // [nrows] the revCond mask the structure was built from
+  int64_t csc_len = 0, csc_ncols = 0;
+  int excl_begin = 0, csc_dup = 0;
   // row split (only when >= 1/64 of the rows have n0 <= 1, e.g. `zy` layouts)
   bool shard_arrays = false;          // revNN/revCond were given for the shard rows only
   bool split = false;
@@ -450,7 +458,7 @@ static void free_handle(gpv_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
-  cudaFree(h->d_obsrank); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
+  cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
   cudaFree(h->d_trivlist); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
   cudaFree(h->d_zloc); cudaFree(h->d_flag); cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
@@ -497,9 +505,14 @@ static gpv_status upload_cond(gpv_handle* h, const void* host) {
   return GPV_OK;
 }
 
+static gpv_status ensure_csc(gpv_handle* h);   // gpv_csc.inc
 extern "C" gpv_status gpv_set_revcond(gpv_handle* h, const void* revCond, gpv_cond_type cond_type) {
   if (!h || !revCond) return fail(GPV_ERR_ARG, "gpv_set_revcond: null argument");
   CUDA_TRY(cudaSetDevice(h->device));
+  // U's pattern belongs to the vecchia.approx, i.e. to the revCond given at create time: createU.R:83-86
+  // changes revCond for one U_NZentries call only and still assembles with U.prep's indices.  Freeze the
+  // compressed-column structure before the first overwrite (gpv_csc.inc keeps its own copy of the mask).
+  if (h->have_obs && h->cond_uploaded && !h->csc_ready) (void)ensure_csc(h);
   if (h->nrows == 0) return GPV_OK;
   if (cond_type == GPV_COND_RLOGICAL_I32) return upload_cond<int32_t>(h, revCond);
   if (cond_type == GPV_COND_F64) return upload_cond<double>(h, revCond);
@@ -725,7 +738,8 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_f, flag + (Nlocs - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp); cudaFree(flag); cudaFree(excl); cudaFree(scan_tmp);
+    cudaFree(tmp); cudaFree(flag); cudaFree(scan_tmp);
+    if (e != cudaSuccess) cudaFree(excl); else h->d_obs_excl = excl;
     H_TRY(e);
     h->n_obs = (int64_t)last_e + last_f;
     h->have_obs = true;
@@ -751,6 +765,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   }
   *out = h;
   gpv_status st = gpv_set_revcond(h, revCond, cond_type);
+  h->cond_uploaded = true;
   if (st != GPV_OK) { free_handle(h); *out = nullptr; return st; }
   return GPV_OK;
 #undef H_TRY
@@ -1304,3 +1319,5 @@ extern "C" double gpv_selftest_table_eval_host(double w, double sig2, double ran
   if (w >= t.w_split) acc *= std::exp(-std::sqrt(w) * cs.q.inv_range);
   return acc;
 }
+
+#include "gpv_csc.inc"

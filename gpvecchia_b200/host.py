@@ -162,6 +162,39 @@ class UHandle:
                                       C.byref(nfail), C.byref(first)))
         return out, int(nfail.value), int(first.value)
 
+    def csc_dims(self):
+        """(ncols, nnz, size): U columns covered by this shard, their nonzeros, N + n."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib.gpv_csc_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def u_sparsity(self):
+        """colindices, rowpointers of R/U_sparsity.R:36-73 (1-based int32) for this shard's rows."""
+        _, nnz, _ = self.csc_dims()
+        ci, rp = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.int32)
+        check(lib.gpv_u_sparsity(self._h, _ptr(ci), _ptr(rp)))
+        return ci, rp
+
+    def csc_pattern(self):
+        """dgCMatrix@p, @i (0-based int32) of the U columns of this shard's rows."""
+        ncols, nnz, _ = self.csc_dims()
+        colptr, rowidx = np.empty(ncols + 1, dtype=np.int32), np.empty(nnz, dtype=np.int32)
+        check(lib.gpv_u_csc_pattern(self._h, _ptr(colptr), _ptr(rowidx)))
+        return colptr, rowidx
+
+    def values_csc(self, covType, covparms, nuggets, nuggets_obsord, out=None):
+        """dgCMatrix@x of the U columns of this shard's rows (createU.R:152-161 in one call)."""
+        cov, nug, tau = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord)
+        _, nnz, _ = self.csc_dims()
+        if out is None:
+            out = np.empty(nnz, dtype=np.float64)
+        elif out.size < nnz or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array of nnz doubles")
+        nfail, first = C.c_int64(0), C.c_int64(-1)
+        check(lib.gpv_u_values_csc(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau), tau.size,
+                                   _ptr(out), C.byref(nfail), C.byref(first)))
+        return out, int(nfail.value), int(first.value)
+
     def loglik_numerator(self, covType, covparms, nuggets, nuggets_obsord, zord, skip_rows=0,
                          include_obs_terms=-1):
         """(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, fused on the GPU."""
@@ -393,7 +426,10 @@ def _prepare_nuggets(va, nuggets):
     return n, size, latent, ord_, obs, nuggets, nuggets_all_ord, nuggets_ord
 
 
-def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0):
+def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0, assemble="csc"):
+    """createU (R/createU.R:65-201, non-MRA branch).  assemble = "csc": the device delivers the slots of
+    the compressed-column matrix (gpv_u_values_csc / gpv_u_csc_pattern); "triplet": the reference's route,
+    packed values + sparseMatrix(i, j, x) (:158-161).  Same matrix either way."""
     va = vecchia_approx
     prep = va["U_prep"]
     if va.get("conditioning", "NN") == "mra":
@@ -410,9 +446,19 @@ def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0):
         revCond[np.isin(prep["revNNarray"], zero_ids) & (prep["revNNarray"] != NA_INT)] = 1
         h.set_revcond(revCond)
         restore = True
+    U = None
     try:
-        # the device writes allLentries = c(c(t(Lentries))[not.na], Zentries) directly (:158-160)
-        allLentries, nfail, first_fail = h.values_packed(covmodel, covparms, nuggets_all_ord, nuggets_ord)
+        if assemble == "csc":
+            try:
+                colptr, rowidx = h.csc_pattern()
+                x, nfail, first_fail = h.values_csc(covmodel, covparms, nuggets_all_ord, nuggets_ord)
+                U = sp.csc_matrix((x, rowidx, colptr), shape=(size, size))
+            except _lib.GpvError as e:
+                if e.status != _lib.GPV_ERR_UNSUPPORTED:
+                    raise
+        if U is None:
+            # the device writes allLentries = c(c(t(Lentries))[not.na], Zentries) directly (:158-160)
+            allLentries, nfail, first_fail = h.values_packed(covmodel, covparms, nuggets_all_ord, nuggets_ord)
     finally:
         if restore:
             h.set_revcond(prep["revCond"])
@@ -420,9 +466,10 @@ def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0):
         import warnings
         warnings.warn(f"Cholesky decomposition failed for {nfail} conditioning set(s) "
                       f"(first at row {first_fail + 1}); those rows of U are zero")
-    U = sp.coo_matrix((allLentries, (prep["colindices"] - 1, prep["rowpointers"] - 1)),
-                      shape=(size, size)).tocsc()                      # :161-162
-    U.sum_duplicates()
+    if U is None:
+        U = sp.coo_matrix((allLentries, (prep["colindices"] - 1, prep["rowpointers"] - 1)),
+                          shape=(size, size)).tocsc()                  # :161-162
+        U.sum_duplicates()
     if va["cond_yz"] == "zy":                                          # :166-171
         keep = np.ones(size, dtype=bool)
         keep[2 * np.arange(n)] = False

@@ -95,6 +95,29 @@ gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, const double*
                                int64_t n, int zentries_tail, double* out, int64_t* nfail,
                                int64_t* first_fail);
 
+/* ---- sparsity arrays and compressed-column output --------------------------
+ * Need `obs` at create time.  For a handle that covers all rows these are the arguments of
+ * Matrix::sparseMatrix at R/createU.R:161 and the slots of the dgCMatrix it returns; for a shard
+ * they are the slices that belong to the shard's rows (= a contiguous range of U's columns).
+ *
+ * gpv_csc_dims: ncols = U columns covered (rows of the shard + observed rows of the shard), nnz = their
+ *   nonzeros (= gpv_packed_len + 2 * observed rows of the shard), size = N + n (U_sparsity.R:12).
+ * gpv_u_sparsity: colindices[nnz], rowpointers[nnz], 1-based, in the value order of
+ *   gpv_u_values_packed(.., zentries_tail = 1): the loops of R/U_sparsity.R:36-73, bit-identical
+ *   (`colindices` is what createU passes as i =, `rowpointers` as j =).
+ * gpv_u_csc_pattern: colptr[ncols + 1] (0-based, relative to the shard's first nonzero) and
+ *   rowidx[nnz] (0-based U rows, ascending inside a column): dgCMatrix@p and @i.
+ * gpv_u_values_csc: x[nnz] in that order (dgCMatrix@x): the kernel, the mask/transpose/concatenate
+ *   of createU.R:158-160 and the triplet sort of sparseMatrix in one call.
+ * A conditioning set that names the same U row twice (sparseMatrix would sum the two values) makes
+ * the last two return GPV_ERR_UNSUPPORTED; gpv_u_sparsity + gpv_u_values_packed still apply. */
+gpv_status gpv_csc_dims(gpv_handle* h, int64_t* ncols, int64_t* nnz, int64_t* size);
+gpv_status gpv_u_sparsity(gpv_handle* h, int32_t* colindices, int32_t* rowpointers);
+gpv_status gpv_u_csc_pattern(gpv_handle* h, int32_t* colptr, int32_t* rowidx);
+gpv_status gpv_u_values_csc(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
+                            const double* nuggets, const double* nuggets_obsord, int64_t n, double* x,
+                            int64_t* nfail, int64_t* first_fail);
+
 /* ---- fused U + likelihood numerator (vecchia_likelihood.R:74-76), no U materialisation -------
  * zord[n] = z[ord.z].  skip_rows: the first skip_rows locations are `zy` dummies whose latent
  * column createU.R:166-171 drops (0 otherwise).  out[0] = quadform.num contribution,

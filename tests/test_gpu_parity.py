@@ -228,6 +228,70 @@ def test_nan_coordinate_fails_exactly_the_rows_that_see_it(m, cov, cp):
     assert _rowscaled_err(got["Lentries"][~sees], ref["Lentries"][~sees]) < VAL_TOL
 
 
+@pytest.mark.parametrize("cond_yz", ["z", "y", "SGV", "zy"])
+def test_native_sparsity_and_csc_output(cond_yz):
+    # U_sparsity's triplet arrays (R/U_sparsity.R:36-73) and the dgCMatrix slots of
+    # sparseMatrix(i, j, x) (R/createU.R:161) from the library, bit-exact against the restated R loops
+    n, m = 500, 9
+    va = _problem(n, m, 2, cond_yz, stream=60)
+    prep = va["U_prep"]
+    N = va["locsord"].shape[0]
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+        ci, rp = h.u_sparsity()
+        assert ci.dtype == np.int32 and np.array_equal(ci, prep["colindices"]) and np.array_equal(rp, prep["rowpointers"])
+        ncols, nnz, size = h.csc_dims()
+        assert size == prep["size"] == ncols and nnz == prep["colindices"].size
+        colptr, rowidx = h.csc_pattern()
+        import scipy.sparse as sp
+        pat = sp.coo_matrix((np.ones(nnz), (prep["colindices"] - 1, prep["rowpointers"] - 1)), shape=(size, size)).tocsc()
+        pat.sort_indices()
+        assert np.array_equal(colptr, pat.indptr) and np.array_equal(rowidx, pat.indices)
+        # shards: the slices of consecutive row ranges concatenate to the full arrays
+        cuts = [0, 1, 130, 131, N]
+        cps, ris, base = [], [], 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"], row_begin=a, row_end=b) as hs:
+                cp_s, ri_s = hs.csc_pattern()
+                cps.append(cp_s[:-1].astype(np.int64) + base); base += int(cp_s[-1]); ris.append(ri_s)
+        assert np.array_equal(np.concatenate(cps + [[base]]), colptr) and np.array_equal(np.concatenate(ris), rowidx)
+    tau = H.make_nuggets(n, stream=60)
+    cp = [1.3, 0.15, 1.5]
+    A = G.createU(va, cp, tau, assemble="csc")["U"]
+    B = G.createU(va, cp, tau, assemble="triplet")["U"]
+    A.sort_indices(); B.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+    Cm = O.createU(va, cp, tau)["U"].tocsc(); Cm.sort_indices()
+    assert np.array_equal(A.indptr, Cm.indptr) and np.array_equal(A.indices, Cm.indices)
+    # values: column-scaled (a column of U is one conditioning set); latent conditioning without nugget
+    # is ill conditioned at this range, so the bound is cond * eps, not VAL_TOL
+    colmax = np.maximum.reduceat(np.abs(Cm.data), Cm.indptr[:-1])
+    assert (np.abs(A.data - Cm.data) / np.repeat(colmax, np.diff(Cm.indptr))).max() < 1e-8
+
+
+def test_csc_values_at_scale_match_packed_order():
+    # n = 2e5, m = 30: x[perm] == packed values exactly, the permutation being the one the pattern implies
+    n, m = 200_000, 30
+    locs = H.make_locs(n, 2, stream=61)
+    revNN = H.ordered_nn_gpu(locs, m)
+    revCond = np.zeros(revNN.shape, dtype=np.int32)
+    revCond[revNN == 0] = np.iinfo(np.int32).min
+    revCond[:, -1] = 1
+    nug = H.make_nuggets(n, stream=61)
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    with G.UHandle(locs, revNN, revCond, obs=np.ones(n, dtype=np.int32)) as h:
+        packed, _, _ = h.values_packed("matern", cp, nug, nug)
+        x, nf, _ = h.values_csc("matern", cp, nug, nug)
+        ci, rp = h.u_sparsity()
+        colptr, rowidx = h.csc_pattern()
+    assert nf == 0 and x.size == packed.size
+    import scipy.sparse as sp
+    size = 2 * n
+    M = sp.csc_matrix((x, rowidx, colptr), shape=(size, size))
+    T = sp.coo_matrix((packed, (ci - 1, rp - 1)), shape=(size, size)).tocsc()
+    T.sort_indices()
+    assert np.array_equal(M.indptr, T.indptr) and np.array_equal(M.indices, T.indices) and np.array_equal(M.data, T.data)
+
+
 def test_zero_nugget_createU_trimming():
     n, m = 300, 6
     va = _problem(n, m, 2, "SGV", stream=51)
