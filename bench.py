@@ -397,6 +397,24 @@ def main():
     # ---- extras: loglik evals/sec (fused numerator, scalars out), other covariances ----------------
     extras = {}
     if not args.no_extras:
+        # the same end-to-end call delivering dgCMatrix@x (compressed-column order)
+        try:
+            ncols, nnz_csc, _ = h.csc_dims()
+            host_csc = torch.empty(nnz_csc, dtype=torch.float64).pin_memory().numpy()
+            for _ in range(2):
+                h.values_csc(covType, covparms, nug_np, tau_np, out=host_csc)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                h.values_csc(covType, covparms, nug_np, tau_np, out=host_csc)
+            barrier()
+            t_csc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_csc, op=dist.ReduceOp.MAX)
+            extras["e2e_csc_sets_per_s"] = n_sets * e2e_steps / float(t_csc.item())
+            del host_csc
+        except G.GpvError as e:                      # duplicate U rows in a set: triplet route only
+            extras["e2e_csc_sets_per_s"] = None
         ll_steps = max(5, args.steps // 2)
 
         def step_ll():

@@ -444,6 +444,8 @@ struct gpv_handle {
   int nchunks = 0;
   int64_t chunk_set[kChunks + 1] = {};   // first set of each chunk
   int64_t chunk_out[kChunks + 1] = {};   // packed output offset where each chunk's rows start
+  int64_t chunk_row[kChunks + 1] = {};   // first (shard-local) row of each chunk
+  int64_t chunk_csc[kChunks + 1] = {};   // compressed-column offset where each chunk's columns start (ensure_csc)
   cudaEvent_t chunk_done[kChunks] = {};
   static const int kRing = 128;
   cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
@@ -755,12 +757,15 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     for (int c = 0; c <= nc; ++c) h->chunk_set[c] = nsets * c / nc;
     h->chunk_out[0] = 0;
     h->chunk_out[nc] = h->packed_len;
+    h->chunk_row[0] = 0;
+    h->chunk_row[nc] = h->nrows;
     for (int c = 1; c < nc; ++c) {
       int32_t row = (int32_t)h->chunk_set[c];
       if (h->split) H_TRY(cudaMemcpy(&row, h->d_rowmap + h->chunk_set[c], sizeof(int32_t), cudaMemcpyDeviceToHost));
       int64_t off = 0;
       H_TRY(cudaMemcpy(&off, h->d_row_off + row, sizeof(int64_t), cudaMemcpyDeviceToHost));
       h->chunk_out[c] = off;
+      h->chunk_row[c] = row;
     }
   }
   *out = h;

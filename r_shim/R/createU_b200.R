@@ -30,6 +30,22 @@ createU_values_b200 <- function(vecchia.approx, covparms, nuggets.all.ord, nugge
                        x = allLentries, dims = c(size, size))
 }
 
+## same, without Matrix::sparseMatrix: the library returns the slots of the dgCMatrix (pattern once per
+## vecchia.approx, values per call).  Falls back to the triplet route if a conditioning set names the same
+## U row twice (the library then reports "unsupported").
+createU_csc_b200 <- function(vecchia.approx, covparms, nuggets.all.ord, nuggets.ord, covmodel, zero.nuggets) {
+  h <- .b200_handle(vecchia.approx)
+  cache <- vecchia.approx$U.prep$b200
+  if (is.null(cache$pattern)) cache$pattern <- .Call("_GPvecchia_b200_csc_pattern", h)
+  if (zero.nuggets) {
+    .Call("_GPvecchia_b200_set_revcond", h, vecchia.approx$U.prep$revCond)
+    on.exit(.Call("_GPvecchia_b200_set_revcond", h, vecchia.approx$U.prep$revCond.orig))
+  }
+  x <- .Call("_GPvecchia_b200_U_values_csc", h, covmodel, covparms, nuggets.all.ord, nuggets.ord)
+  size <- as.integer(cache$pattern[[3]])
+  methods::new("dgCMatrix", p = cache$pattern[[1]], i = cache$pattern[[2]], x = x, Dim = c(size, size))
+}
+
 ## optional: numerator of vecchia_likelihood_U (R/vecchia_likelihood.R:74-76) without building U
 loglik_numerator_b200 <- function(z, vecchia.approx, covparms, nuggets.all.ord, nuggets.ord, covmodel) {
   h <- .b200_handle(vecchia.approx)

@@ -111,6 +111,48 @@ SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_or
   return out;
 }
 
+/* dgCMatrix slots of U: list(p, i, size) once per vecchia.approx ... */
+SEXP gpvb200_csc_pattern(SEXP ptr) {
+  gpv_handle* h = get_handle(ptr);
+  int64_t ncols = 0, nnz = 0, size = 0;
+  check(gpv_csc_dims(h, &ncols, &nnz, &size));
+  SEXP p = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)(ncols + 1)));
+  SEXP i = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+  check(gpv_u_csc_pattern(h, INTEGER(p), INTEGER(i)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, p);
+  SET_VECTOR_ELT(out, 1, i);
+  SET_VECTOR_ELT(out, 2, Rf_ScalarReal((double)size));
+  UNPROTECT(3);
+  return out;
+}
+/* ... and @x per createU call: kernel + createU.R:158-160 + the triplet sort of sparseMatrix (:161) */
+SEXP gpvb200_U_values_csc(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
+  gpv_handle* h = get_handle(ptr);
+  int64_t nnz = 0, nfail = 0, first = -1;
+  check(gpv_csc_dims(h, NULL, &nnz, NULL));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+  check(gpv_u_values_csc(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                         REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first));
+  warn_fail(nfail, first);
+  UNPROTECT(1);
+  return out;
+}
+/* list(colindices, rowpointers) of R/U_sparsity.R:36-73 */
+SEXP gpvb200_U_sparsity(SEXP ptr) {
+  gpv_handle* h = get_handle(ptr);
+  int64_t nnz = 0;
+  check(gpv_csc_dims(h, NULL, &nnz, NULL));
+  SEXP ci = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+  SEXP rp = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+  check(gpv_u_sparsity(h, INTEGER(ci), INTEGER(rp)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, ci);
+  SET_VECTOR_ELT(out, 1, rp);
+  UNPROTECT(3);
+  return out;
+}
+
 /* c(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, no U materialisation */
 SEXP gpvb200_loglik_numerator(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord,
                               SEXP nuggets_ord, SEXP zord, SEXP skip_rows) {
@@ -136,6 +178,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_b200_create", (DL_FUNC)&gpvb200_create, 4},
     {"_GPvecchia_b200_set_revcond", (DL_FUNC)&gpvb200_set_revcond, 2},
     {"_GPvecchia_b200_U_values", (DL_FUNC)&gpvb200_U_values, 5},
+    {"_GPvecchia_b200_csc_pattern", (DL_FUNC)&gpvb200_csc_pattern, 1},
+    {"_GPvecchia_b200_U_values_csc", (DL_FUNC)&gpvb200_U_values_csc, 5},
+    {"_GPvecchia_b200_U_sparsity", (DL_FUNC)&gpvb200_U_sparsity, 1},
     {"_GPvecchia_b200_loglik_numerator", (DL_FUNC)&gpvb200_loglik_numerator, 7},
     {"_GPvecchia_b200_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},
     {NULL, NULL, 0}};
