@@ -44,9 +44,9 @@ def summary(rep, tag, sets):
     open(os.path.join(pr, f"r01_{tag}_details.txt"), "w").write("\n".join(l for l in det.splitlines() if l.strip()))
     return s
 
-c = summary(os.path.join(go, "prof_closed.ncu-rep"), "u_quad_closed_P31_D2_nu15", 1e6)
-g = summary(os.path.join(go, "prof_general.ncu-rep"), "u_quad_general_P31_D2_nu08", 1e6)
-json.dump({"kernel": c["kernel"], "source": "profiles/r01_u_quad_closed_P31_D2_nu15_summary.json",
+c = summary(os.path.join(go, "prof_closed.ncu-rep"), "u_band_closed_P31_D2_nu15", 1e6)
+g = summary(os.path.join(go, "prof_general.ncu-rep"), "u_band_general_P31_D2_nu08", 1e6)
+json.dump({"kernel": c["kernel"], "source": "profiles/r01_u_band_closed_P31_D2_nu15_summary.json",
            "dram_bytes_per_launch": c["dram_bytes_per_launch"],
            "fp64_pipe_pct_of_peak_active": c["fp64_pipe_pct_of_peak_active"]},
           open(os.path.join(pr, "roofline_traffic.json"), "w"), indent=1)
