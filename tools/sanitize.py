@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import gpvecchia_b200 as G
 from gpvecchia_b200 import harness as H
 
-for (n, m, d, layout) in ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"), (500, 9, 2, "zy"), (200, 5, 5, "z")):
+for (n, m, d, layout) in ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"), (500, 9, 2, "zy"), (200, 5, 5, "z"),
+                          (300, 20, 2, "z"), (300, 25, 2, "z"), (300, 31, 2, "z"), (300, 40, 3, "z"), (300, 20, 3, "zy")):
     locs = H.make_locs(n, d, stream=1)
     if layout == "zy":
         locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
@@ -22,7 +23,9 @@ for (n, m, d, layout) in ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"
                        ("matern", [1.0, 0.2, 0.8]), ("esqe", [0.7, 0.2, 0.4, 0.1])):
             h.U_NZentries(ct, cp, nug_all, tau)
             h.values_packed(ct, cp, nug_all, tau)
+            h.values_csc(ct, cp, nug_all, tau)
             h.loglik_numerator(ct, cp, nug_all, tau, z, skip_rows=n if layout == "zy" else 0)
+        h.u_sparsity(); h.csc_pattern()
         if layout == "z":
             h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all, tau, z)
 G.MaternFun(np.linspace(0, 3, 100), [1.0, 0.3, 1.3])
