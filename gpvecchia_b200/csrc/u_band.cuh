@@ -21,6 +21,14 @@
 
 namespace gpv {
 
+#ifndef GPV_BAND_PAIR_UNROLL
+#define GPV_BAND_PAIR_UNROLL 1
+#endif
+#ifndef GPV_BAND_MINB3
+#define GPV_BAND_MINB3 3
+#endif
+constexpr int kBandPairUnroll = GPV_BAND_PAIR_UNROLL;   // pair-stage iterations per loop trip
+
 template <int G, int P, int D>
 struct BandLayout {
   static constexpr int NB = (P + G - 1) / G;               // bands: 3 or 4
@@ -47,7 +55,7 @@ struct BandLayout {
   static constexpr int kDoubles = ((kRaw + 15) / 16) * 16 + 16;
   static constexpr int kBytesPerBlock = kDoubles * 8 * kSetsPerWarp * kWarpsPerBlock;
   // resident blocks the register allocation is sized for: three bands of a G = 8 group fit 168 registers
-  static constexpr int kMinBlocks = (G == 8 && NB == 3) ? 3 : 2;
+  static constexpr int kMinBlocks = (G == 8 && NB == 3) ? GPV_BAND_MINB3 : 2;
   static_assert(G == 8 || G == 16, "lane groups of 8 or 16");
   static_assert(P > 2 * G && P <= 4 * G, "band-folded kernel: 2G < P <= 4G");
   static_assert(G == 8 || NB == 3, "four bands of 16 lanes do not fit the register file");
@@ -101,7 +109,7 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
   const uint4* stab_lane = stab + gl;
   char* Asb = reinterpret_cast<char*>(As);
   const double guard = (KIND == COV_GENERAL) ? 0.0 : kMathC[7];
-#pragma unroll 1
+#pragma unroll kBandPairUnroll
   for (int t = 1; t <= LY::kT; ++t) {
     const uint4 offs = stab_lane[(t - 1) * G];
     const int jp[4] = {(int)(offs.z & 0xffffu), (int)(offs.z >> 16), (int)(offs.w & 0xffffu), (int)(offs.w >> 16)};
