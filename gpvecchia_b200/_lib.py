@@ -19,6 +19,7 @@ EXPORTED = [
     "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_create_shard", "gpv_destroy",
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
     "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
+    "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
@@ -70,6 +71,12 @@ def _load():
     L.gpv_u_csc_pattern.restype = i32
     L.gpv_u_values_csc.argtypes = [vp, cp, vp, i32, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i64)]
     L.gpv_u_values_csc.restype = i32
+    L.gpv_multi_csc_dims.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_multi_csc_dims.restype = i32
+    L.gpv_multi_u_csc_pattern.argtypes = [vp, vp, vp]
+    L.gpv_multi_u_csc_pattern.restype = i32
+    L.gpv_multi_u_values_csc.argtypes = [vp, cp, vp, i32, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_multi_u_values_csc.restype = i32
     L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
     L.gpv_loglik_numerator.restype = i32
     L.gpv_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i32, vp]

@@ -137,6 +137,76 @@ extern "C" gpv_status gpv_multi_u_values_packed(gpv_multi* m, const char* covTyp
   return GPV_OK;
 }
 
+// ---- compressed-column output over several devices -------------------------------------------------
+// The U columns of consecutive row shards are consecutive column ranges, so every device writes its
+// slice of dgCMatrix@i / @x in place; the column pointers of shard i are shifted by the nonzeros before.
+static gpv_status multi_csc_offsets(gpv_multi* m, std::vector<int64_t>* col0, std::vector<int64_t>* nz0, int64_t* size) {
+  const int nd = (int)m->h.size();
+  col0->assign(nd + 1, 0); nz0->assign(nd + 1, 0);
+  for (int i = 0; i < nd; ++i) {
+    int64_t nc = 0, nz = 0, sz = 0;
+    gpv_status st = gpv_csc_dims(m->h[i], &nc, &nz, &sz);
+    if (st != GPV_OK) return st;
+    (*col0)[i + 1] = (*col0)[i] + nc;
+    (*nz0)[i + 1] = (*nz0)[i] + nz;
+    if (size) *size = sz;
+  }
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_multi_csc_dims(gpv_multi* m, int64_t* ncols, int64_t* nnz, int64_t* size) {
+  if (!m) { gpv_set_last_error("gpv_multi_csc_dims: null handle"); return GPV_ERR_ARG; }
+  std::vector<int64_t> c0, z0;
+  gpv_status st = multi_csc_offsets(m, &c0, &z0, size);
+  if (st != GPV_OK) return st;
+  if (ncols) *ncols = c0.back();
+  if (nnz) *nnz = z0.back();
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_multi_u_csc_pattern(gpv_multi* m, int32_t* colptr, int32_t* rowidx) {
+  if (!m || !colptr || !rowidx) { gpv_set_last_error("gpv_multi_u_csc_pattern: null argument"); return GPV_ERR_ARG; }
+  std::vector<int64_t> c0, z0;
+  gpv_status st = multi_csc_offsets(m, &c0, &z0, nullptr);
+  if (st != GPV_OK) return st;
+  if (z0.back() > 2147483647LL) { gpv_set_last_error("matrix too large for 32-bit dgCMatrix indices"); return GPV_ERR_UNSUPPORTED; }
+  const int nd = (int)m->h.size();
+  // shard i fills colptr[c0[i] .. c0[i+1]] relative to its own first nonzero; the shared boundary entry
+  // is rewritten by the next shard with the same value after the shift, so shift from the last shard down
+  st = run_all(nd, [&](int i) {
+    std::vector<int32_t> cp((size_t)(c0[i + 1] - c0[i] + 1));
+    gpv_status s2 = gpv_u_csc_pattern(m->h[i], cp.data(), rowidx + z0[i]);
+    if (s2 != GPV_OK) return s2;
+    for (int64_t c = 0; c < c0[i + 1] - c0[i]; ++c) colptr[c0[i] + c] = (int32_t)(cp[(size_t)c] + z0[i]);
+    if (i == nd - 1) colptr[c0[nd]] = (int32_t)z0[nd];
+    return GPV_OK;
+  });
+  return st;
+}
+
+extern "C" gpv_status gpv_multi_u_values_csc(gpv_multi* m, const char* covType, const double* covparms, int ncov,
+                                             const double* nuggets, const double* nuggets_obsord, int64_t n,
+                                             double* x, int64_t* nfail, int64_t* first_fail) {
+  if (!m || !x) { gpv_set_last_error("gpv_multi_u_values_csc: null argument"); return GPV_ERR_ARG; }
+  std::vector<int64_t> c0, z0;
+  gpv_status st = multi_csc_offsets(m, &c0, &z0, nullptr);
+  if (st != GPV_OK) return st;
+  const int nd = (int)m->h.size();
+  std::vector<int64_t> nf(nd, 0), ff(nd, -1);
+  st = run_all(nd, [&](int i) {
+    return gpv_u_values_csc(m->h[i], covType, covparms, ncov, nuggets, nuggets_obsord, n, x + z0[i], &nf[i], &ff[i]);
+  });
+  if (st != GPV_OK) return st;
+  int64_t tot = 0, first = -1;
+  for (int i = 0; i < nd; ++i) {
+    tot += nf[i];
+    if (nf[i] > 0 && (first < 0 || ff[i] < first)) first = ff[i];
+  }
+  if (nfail) *nfail = tot;
+  if (first_fail) *first_fail = first;
+  return GPV_OK;
+}
+
 extern "C" gpv_status gpv_multi_loglik_numerator(gpv_multi* m, const char* covType, const double* covparms,
                                                  int ncov, const double* nuggets,
                                                  const double* nuggets_obsord, const double* zord,

@@ -302,6 +302,27 @@ class MultiHandle:
                                             C.byref(nfail), C.byref(first)))
         return out, int(nfail.value), int(first.value)
 
+    def csc_dims(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib.gpv_multi_csc_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def csc_pattern(self):
+        ncols, nnz, _ = self.csc_dims()
+        colptr, rowidx = np.empty(ncols + 1, dtype=np.int32), np.empty(nnz, dtype=np.int32)
+        check(lib.gpv_multi_u_csc_pattern(self._h, _ptr(colptr), _ptr(rowidx)))
+        return colptr, rowidx
+
+    def values_csc(self, covType, covparms, nuggets, nuggets_obsord, out=None):
+        cov, nug, tau = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord)
+        _, nnz, _ = self.csc_dims()
+        if out is None:
+            out = np.empty(nnz, dtype=np.float64)
+        nfail, first = C.c_int64(0), C.c_int64(-1)
+        check(lib.gpv_multi_u_values_csc(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau),
+                                         tau.size, _ptr(out), C.byref(nfail), C.byref(first)))
+        return out, int(nfail.value), int(first.value)
+
     def loglik_numerator(self, covType, covparms, nuggets, nuggets_obsord, zord, skip_rows=0):
         cov, nug, tau, z = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord), _f64(zord)
         out = np.zeros(3, dtype=np.float64)

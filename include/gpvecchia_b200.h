@@ -188,6 +188,13 @@ gpv_status gpv_multi_loglik_numerator(gpv_multi* m, const char* covType, const d
 gpv_status gpv_multi_loglik_z(gpv_multi* m, const char* covType, const double* covparms, int ncovparms,
                               const double* nuggets, const double* nuggets_obsord, const double* zord,
                               int64_t n, double out[6]);
+/* compressed-column output over the devices (see gpv_u_csc_pattern / gpv_u_values_csc): same arrays as a
+ * single full-range handle returns, every device filling the slice of its row shard */
+gpv_status gpv_multi_csc_dims(gpv_multi* m, int64_t* ncols, int64_t* nnz, int64_t* size);
+gpv_status gpv_multi_u_csc_pattern(gpv_multi* m, int32_t* colptr, int32_t* rowidx);
+gpv_status gpv_multi_u_values_csc(gpv_multi* m, const char* covType, const double* covparms, int ncovparms,
+                                  const double* nuggets, const double* nuggets_obsord, int64_t n, double* x,
+                                  int64_t* nfail, int64_t* first_fail);
 /* sets the calling thread's gpv_last_error() text (used by the multi-GPU front end) */
 void gpv_set_last_error(const char* msg);
 

@@ -698,12 +698,17 @@ def test_single_process_multi_device_front_end(layout):
         want, nf, _ = h.values_packed("matern", cp, nug_all, tau)
         q, l, _ = h.loglik_numerator("matern", cp, nug_all, tau, z, skip_rows=skip)
         llz = h.loglik_z("matern", cp, nug_all, tau, z) if layout == "z" else None
+        want_p, want_i = h.csc_pattern()
+        want_x, _, _ = h.values_csc("matern", cp, nug_all, tau)
     ndev = G.lib.gpv_device_count()
     for devices in ([0], [0, 0, 0], list(range(ndev)) * 2):
         with G.MultiHandle(locs2, revNN, revCond, obs=obs, devices=devices) as mh:
             assert mh.row_cuts[0] == 0 and mh.row_cuts[-1] == locs2.shape[0] and mh.packed_len == want.size - 2 * n
             got, nf2, _ = mh.values_packed("matern", cp, nug_all, tau)
             assert nf2 == nf and np.array_equal(got, want)
+            got_p, got_i = mh.csc_pattern()
+            got_x, nf3, _ = mh.values_csc("matern", cp, nug_all, tau)
+            assert nf3 == nf and np.array_equal(got_p, want_p) and np.array_equal(got_i, want_i) and np.array_equal(got_x, want_x)
             q2, l2, _ = mh.loglik_numerator("matern", cp, nug_all, tau, z, skip_rows=skip)
             assert abs(q2 - q) <= 1e-12 * abs(q) and abs(l2 - l) <= 1e-12 * abs(l)
             if layout == "z":
