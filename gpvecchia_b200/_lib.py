@@ -22,7 +22,7 @@ EXPORTED = [
     "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
-    "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn",
+    "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn", "gpv_whichCondOnLatent",
     "gpv_multi_create", "gpv_multi_destroy", "gpv_multi_num_devices", "gpv_multi_packed_len",
     "gpv_multi_row_cuts", "gpv_multi_set_revcond", "gpv_multi_u_values_packed",
     "gpv_multi_loglik_numerator", "gpv_multi_loglik_z", "gpv_set_last_error",
@@ -77,6 +77,8 @@ def _load():
     L.gpv_multi_u_csc_pattern.restype = i32
     L.gpv_multi_u_values_csc.argtypes = [vp, cp, vp, i32, vp, vp, i64, vp, C.POINTER(i64), C.POINTER(i64)]
     L.gpv_multi_u_values_csc.restype = i32
+    L.gpv_whichCondOnLatent.argtypes = [vp, i64, i32, i64, vp]
+    L.gpv_whichCondOnLatent.restype = i32
     L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
     L.gpv_loglik_numerator.restype = i32
     L.gpv_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i32, vp]

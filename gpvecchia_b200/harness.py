@@ -183,6 +183,19 @@ def layout_zy_pred(locs_obs, locs_pred, m, device=0, use_gpu=True):
     return np.vstack([locs_obs, locs_all]), NNarray, Cond, obs
 
 
+def whichCondOnLatent(NNarray, firstind_pred=None):
+    """R/whichCondOnLatent.R through the library's host routine (gpv_whichCondOnLatent): NNarray is the
+    un-reversed neighbour array (1-based, 0 / NA = missing); returns int8 1 / 0 / -1 (NA) like the
+    restatement in oracle/vecchia_np.py."""
+    NN = np.asarray(NNarray)
+    n, p = NN.shape
+    nn32 = np.asfortranarray(np.where(NN <= 0, np.iinfo(np.int32).min, NN).astype(np.int32))
+    out = np.empty((n, p), dtype=np.int32, order="F")
+    check(lib.gpv_whichCondOnLatent(nn32.ctypes.data_as(C.c_void_p), n, p, 0 if firstind_pred is None else int(firstind_pred),
+                                    out.ctypes.data_as(C.c_void_p)))
+    return np.where(out == np.iinfo(np.int32).min, -1, out).astype(np.int8)
+
+
 def make_vecchia_approx(locsord, NNarray, Cond, obs, cond_yz, ord_=None, ord_z=None,
                         ord_pred="general", U_sparsity=None):
     """Assemble the vecchia.approx list (vecchia_specify.R:234-236) from harness-made inputs."""

@@ -221,6 +221,14 @@ gpv_status gpv_EsqeFun(const double* dist, int64_t len, const double* covparms, 
 gpv_status gpv_measure_fp64_peak(int device, double* tflops);
 gpv_status gpv_measure_copy_bw(int device, double* gbs);
 
+/* ---- whichCondOnLatent (R/whichCondOnLatent.R:2-27), host code -------------------------------
+ * The sparse-general-Vecchia rule (vecchia_specify.R:183-185): NNarray is the un-reversed n x p neighbour
+ * array, column-major, 1-based, missing = NA_integer_ (or 0); firstind_pred <= 0 means n + 1.
+ * CondOnLatent (n x p, column-major) receives R logicals: 1, 0, NA_integer_.  Sequential over rows like
+ * the reference (row k reads the finished rows of its neighbours); runs on the host, no device needed. */
+gpv_status gpv_whichCondOnLatent(const int32_t* NNarray, int64_t n, int p, int64_t firstind_pred,
+                                 int32_t* CondOnLatent);
+
 /* ---- harness: synthetic inputs at scale (not part of the reference path) -------
  * Ordered m-nearest-neighbour search on the GPU: row i gets (i, its min(m,i) nearest among rows
  * < i, nearest first) -- semantics of GpGp::find_ordered_nn as used at vecchia_specify.R:159 --

@@ -77,3 +77,27 @@ def test_layout_zy_pred_matches_specify_restatement():
     locs2, NN, Cond, obs = H.layout_zy_pred(locs, lp, 8, use_gpu=False)
     assert np.array_equal(NN, va["NNarray"]) and np.array_equal(Cond, va["Cond"])
     assert np.array_equal(obs, va["obs"]) and np.array_equal(locs2, va["locsord"])
+
+
+@pytest.mark.parametrize("seed,n,m,npred", [(0, 120, 5, 0), (1, 300, 12, 0), (2, 90, 30, 0), (3, 150, 7, 40), (4, 40, 3, 25)])
+def test_native_whichCondOnLatent_matches_restated_R_loop(seed, n, m, npred):
+    # gpv_whichCondOnLatent (host C++, merge counts) vs the line-by-line restatement of
+    # R/whichCondOnLatent.R:2-27 in the oracle, with and without prediction locations (firstind.pred)
+    rng = np.random.default_rng(seed)
+    locs = rng.random((n + npred, 2))
+    NN = O.find_ordered_nn_brute(locs, m)
+    first = n + 1 if npred else None
+    ref = O.whichCondOnLatent(NN, first)
+    got = H.whichCondOnLatent(NN, first)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_native_whichCondOnLatent_scales():
+    # n = 2e5, m = 30 in a few seconds (the R loop is O(n m^3) interpreter calls): properties only
+    n, m = 200_000, 30
+    locs = H.make_locs(n, 2, stream=9)
+    NN = H.ordered_nn_kdtree(locs, m)
+    C_ = H.whichCondOnLatent(NN)
+    assert np.all(C_[:, 0] == 1) and np.array_equal(C_ == -1, NN == 0)
+    frac = (C_[m + 1:, 1:] == 1).mean()
+    assert 0.05 < frac < 0.95          # SGV conditions on a mix of y and z
