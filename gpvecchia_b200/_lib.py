@@ -18,7 +18,7 @@ GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
 EXPORTED = [
     "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_create_shard", "gpv_destroy",
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
-    "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
+    "gpv_u_nzentries_mat", "gpv_u_values_packed_mat", "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
     "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
@@ -79,6 +79,10 @@ def _load():
     L.gpv_multi_u_values_csc.restype = i32
     L.gpv_whichCondOnLatent.argtypes = [vp, i64, i32, i64, vp]
     L.gpv_whichCondOnLatent.restype = i32
+    L.gpv_u_nzentries_mat.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_u_nzentries_mat.restype = i32
+    L.gpv_u_values_packed_mat.argtypes = [vp, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.gpv_u_values_packed_mat.restype = i32
     L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
     L.gpv_loglik_numerator.restype = i32
     L.gpv_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i32, vp]

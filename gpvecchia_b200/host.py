@@ -145,6 +145,33 @@ class UHandle:
         return dict(Lentries=L.reshape(self.p, self.nrows).T, Zentries=Z, nfail=int(nfail.value),
                     first_fail=int(first.value))
 
+    def U_NZentries_mat(self, covVals, nuggets_obsord):
+        """U_NZentries_mat (src/U_NZentries.cpp:126-197): `covmodel` given as the N x N covariance matrix."""
+        cv = np.asfortranarray(np.asarray(covVals, dtype=np.float64))
+        if cv.shape != (self.N, self.N):
+            raise ValueError("covVals must be Nlocs x Nlocs")
+        tau = _f64(nuggets_obsord)
+        n = tau.size
+        L = np.empty(self.nrows * self.p, dtype=np.float64)
+        Z = np.empty(2 * n, dtype=np.float64)
+        nfail, first = C.c_int64(0), C.c_int64(-1)
+        check(lib.gpv_u_nzentries_mat(self._h, cv.ctypes.data_as(C.c_void_p), _ptr(tau), n, _ptr(L), _ptr(Z),
+                                      C.byref(nfail), C.byref(first)))
+        return dict(Lentries=L.reshape(self.p, self.nrows).T, Zentries=Z, nfail=int(nfail.value),
+                    first_fail=int(first.value))
+
+    def values_packed_mat(self, covVals, nuggets_obsord, zentries_tail=True):
+        cv = np.asfortranarray(np.asarray(covVals, dtype=np.float64))
+        if cv.shape != (self.N, self.N):
+            raise ValueError("covVals must be Nlocs x Nlocs")
+        tau = _f64(nuggets_obsord)
+        n = tau.size
+        out = np.empty(self.packed_len + (2 * n if zentries_tail else 0), dtype=np.float64)
+        nfail, first = C.c_int64(0), C.c_int64(-1)
+        check(lib.gpv_u_values_packed_mat(self._h, cv.ctypes.data_as(C.c_void_p), _ptr(tau), n,
+                                          1 if zentries_tail else 0, _ptr(out), C.byref(nfail), C.byref(first)))
+        return out, int(nfail.value), int(first.value)
+
     def values_packed(self, covType, covparms, nuggets, nuggets_obsord, zentries_tail=True, out=None):
         """allLentries of createU.R:158-160 for this shard, straight from the device."""
         cov = _f64(covparms)
@@ -455,8 +482,11 @@ def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0, asse
     prep = va["U_prep"]
     if va.get("conditioning", "NN") == "mra":
         raise NotImplementedError("the MRA / ic0 branch (createU.R:89-139) stays in the reference")
-    if not isinstance(covmodel, str):
-        raise TypeError("argument 'covmodel' type not supported")      # createU.R:155 (matrix: stays in R)
+    covmat = None
+    if isinstance(covmodel, np.ndarray) and covmodel.ndim == 2:        # createU.R:149-151: U_NZentries_mat
+        covmat, assemble = covmodel, "triplet"
+    elif not isinstance(covmodel, str):
+        raise TypeError("argument 'covmodel' type not supported")      # createU.R:155
     n, size, latent, ord_, obs, nuggets, nuggets_all_ord, nuggets_ord = _prepare_nuggets(va, nuggets)
     zero_nuggets = bool(np.any(nuggets == 0))
     h = _handle_for(va, device)
@@ -477,7 +507,9 @@ def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0, asse
             except _lib.GpvError as e:
                 if e.status != _lib.GPV_ERR_UNSUPPORTED:
                     raise
-        if U is None:
+        if U is None and covmat is not None:
+            allLentries, nfail, first_fail = h.values_packed_mat(covmat, nuggets_ord)
+        elif U is None:
             # the device writes allLentries = c(c(t(Lentries))[not.na], Zentries) directly (:158-160)
             allLentries, nfail, first_fail = h.values_packed(covmodel, covparms, nuggets_all_ord, nuggets_ord)
     finally:

@@ -95,6 +95,17 @@ gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, const double*
                                int64_t n, int zentries_tail, double* out, int64_t* nfail,
                                int64_t* first_fail);
 
+/* ---- `covmodel` given as a matrix: U_NZentries_mat (src/U_NZentries.cpp:126-197, createU.R:149-151)
+ * covVals: the user's Nlocs x Nlocs covariance of the ordered locations (column-major, host).  Per row
+ * covmat = covVals(inds, inds): like the reference, NO nugget is added and revCond is not read.  Same
+ * outputs, orders and failure semantics as gpv_u_nzentries / gpv_u_values_packed.  Not a throughput
+ * path (the matrix is uploaded per call and caps Nlocs at a few ten thousand). */
+gpv_status gpv_u_nzentries_mat(gpv_handle* h, const double* covVals, const double* nuggets_obsord, int64_t n,
+                               double* Lentries, double* Zentries, int64_t* nfail, int64_t* first_fail);
+gpv_status gpv_u_values_packed_mat(gpv_handle* h, const double* covVals, const double* nuggets_obsord,
+                                   int64_t n, int zentries_tail, double* out, int64_t* nfail,
+                                   int64_t* first_fail);
+
 /* ---- sparsity arrays and compressed-column output --------------------------
  * Need `obs` at create time.  For a handle that covers all rows these are the arguments of
  * Matrix::sparseMatrix at R/createU.R:161 and the slots of the dgCMatrix it returns; for a shard

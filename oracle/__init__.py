@@ -14,11 +14,11 @@ from .ref_c import (MaternFun, EsqeFun, U_NZentries, block_cond_proxy, lib, max_
                     has_lapack, RowsProblem)
 from .vecchia_np import (U_sparsity, createU, vecchia_likelihood, vecchia_likelihood_U, U2V,
                          vecchia_specify, whichCondOnLatent, find_ordered_nn_brute,
-                         loglik_numerator_from_U, exact_loglik, loglik_numerator_rows)
+                         loglik_numerator_from_U, exact_loglik, loglik_numerator_rows, U_NZentries_mat)
 
 __all__ = [
     "MaternFun", "EsqeFun", "U_NZentries", "block_cond_proxy", "lib", "max_threads", "has_lapack", "RowsProblem",
     "U_sparsity", "createU", "vecchia_likelihood", "vecchia_likelihood_U", "U2V",
     "vecchia_specify", "whichCondOnLatent", "find_ordered_nn_brute",
-    "loglik_numerator_from_U", "exact_loglik", "loglik_numerator_rows",
+    "loglik_numerator_from_U", "exact_loglik", "loglik_numerator_rows", "U_NZentries_mat",
 ]

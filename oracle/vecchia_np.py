@@ -132,6 +132,35 @@ def whichCondOnLatent(NNarray, firstind_pred=None):
     return C
 
 
+def U_NZentries_mat(n, revNNarray, covVals, nuggets_obsord):
+    """src/U_NZentries.cpp:126-197 restated (numpy, small cases): covmat = covVals(inds, inds), no nugget,
+    revCond unused; chol(., "upper") + solve(R, e_last); a failing Cholesky leaves the row zero."""
+    rnn = np.asarray(revNNarray)
+    N, p = rnn.shape
+    L = np.zeros((N, p))
+    nfail = 0
+    for k in range(N):
+        inds = rnn[k][(rnn[k] != 0) & (rnn[k] != NA)] - 1
+        n0 = inds.size
+        if n0 == 0:
+            continue
+        cm = np.asarray(covVals)[np.ix_(inds, inds)]
+        try:
+            if not np.all(np.isfinite(cm)):
+                raise np.linalg.LinAlgError
+            R = np.linalg.cholesky(cm).T
+        except np.linalg.LinAlgError:
+            nfail += 1
+            continue
+        e = np.zeros(n0); e[-1] = 1.0
+        L[k, :n0] = np.linalg.solve(R, e)
+    tau = np.asarray(nuggets_obsord, dtype=np.float64)
+    Z = np.empty(2 * n)
+    Z[0::2] = -1.0 / np.sqrt(tau)
+    Z[1::2] = 1.0 / np.sqrt(tau)
+    return dict(Lentries=L, Zentries=Z, nfail=nfail)
+
+
 # ----------------------------------------------------------------------------------------------
 # neighbour search stand-ins (GpGp::find_ordered_nn, FNN::get.knn are third-party inputs)
 # ----------------------------------------------------------------------------------------------

@@ -65,6 +65,39 @@ SEXP gpvb200_U_NZentries(SEXP Ncores, SEXP n, SEXP locs, SEXP revNNarray, SEXP r
   return out;
 }
 
+/* ---- stateless drop-in for the matrix branch: same nine arguments as U_NZentries_mat
+ * (src/RcppExports.cpp: _GPvecchia_U_NZentries_mat; covVals takes the place of covType) -------------- */
+SEXP gpvb200_U_NZentries_mat(SEXP Ncores, SEXP n, SEXP locs, SEXP revNNarray, SEXP revCondOnLatent,
+                             SEXP nuggets, SEXP nuggets_obsord, SEXP covVals, SEXP covparms) {
+  (void)Ncores; (void)nuggets; (void)covparms;               /* unused by the reference too (:126-197) */
+  const int64_t N = Rf_nrows(locs);
+  const int d = Rf_ncols(locs), p = Rf_ncols(revNNarray);
+  const int64_t nobs = (int64_t)Rf_asReal(n);
+  if (!Rf_isReal(covVals) || Rf_nrows(covVals) != N || Rf_ncols(covVals) != N) Rf_error("covmodel must be an N x N numeric matrix");
+  SEXP nn = PROTECT(Rf_coerceVector(revNNarray, INTSXP));
+  const int is_lgl = Rf_isLogical(revCondOnLatent);
+  SEXP rc = PROTECT(is_lgl ? revCondOnLatent : Rf_coerceVector(revCondOnLatent, REALSXP));
+  SEXP L = PROTECT(Rf_allocMatrix(REALSXP, (int)N, p));
+  SEXP Z = PROTECT(Rf_allocMatrix(REALSXP, (int)(2 * nobs), 1));
+  gpv_handle* h = NULL;
+  check(gpv_create(&h, N, p, d, REAL(locs), INTEGER(nn), is_lgl ? (const void*)LOGICAL(rc) : (const void*)REAL(rc),
+                   is_lgl ? GPV_COND_RLOGICAL_I32 : GPV_COND_F64, NULL, 0, N, device_from_option()));
+  int64_t nfail = 0, first = -1;
+  gpv_status st = gpv_u_nzentries_mat(h, REAL(covVals), REAL(nuggets_obsord), nobs, REAL(L), REAL(Z), &nfail, &first);
+  gpv_destroy(h);
+  check(st);
+  warn_fail(nfail, first);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, L);
+  SET_VECTOR_ELT(out, 1, Z);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("Lentries"));
+  SET_STRING_ELT(nm, 1, Rf_mkChar("Zentries"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(6);
+  return out;
+}
+
 /* ---- device-resident handle: one per vecchia.approx ------------------------------------------ */
 static void handle_finalizer(SEXP ptr) {
   gpv_handle* h = (gpv_handle*)R_ExternalPtrAddr(ptr);
@@ -175,6 +208,7 @@ SEXP gpvb200_MaternFun(SEXP distmat, SEXP covparms) {
 static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_U_NZentries", (DL_FUNC)&gpvb200_U_NZentries, 9},   /* same name and arity as
                                                                        src/RcppExports.cpp:159 */
+    {"_GPvecchia_U_NZentries_mat", (DL_FUNC)&gpvb200_U_NZentries_mat, 9},
     {"_GPvecchia_b200_create", (DL_FUNC)&gpvb200_create, 4},
     {"_GPvecchia_b200_set_revcond", (DL_FUNC)&gpvb200_set_revcond, 2},
     {"_GPvecchia_b200_U_values", (DL_FUNC)&gpvb200_U_values, 5},

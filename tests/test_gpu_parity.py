@@ -14,6 +14,7 @@ from gpvecchia_b200 import harness as H
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NA_I32 = np.iinfo(np.int32).min
 VAL_TOL = 1e-10
 LL_TOL = 1e-8
 
@@ -290,6 +291,48 @@ def test_csc_values_at_scale_match_packed_order():
     T = sp.coo_matrix((packed, (ci - 1, rp - 1)), shape=(size, size)).tocsc()
     T.sort_indices()
     assert np.array_equal(M.indptr, T.indptr) and np.array_equal(M.indices, T.indices) and np.array_equal(M.data, T.data)
+
+
+@pytest.mark.parametrize("m,cond_yz", [(8, "z"), (20, "SGV"), (40, "z"), (9, "zy")])
+def test_covmodel_matrix_branch(m, cond_yz):
+    # U_NZentries_mat (src/U_NZentries.cpp:126-197, createU.R:149-151): covmat = covVals(inds, inds), no
+    # nugget added, revCond not read.  Values and packed order vs the restatement; one indefinite
+    # block (a row/column of covVals scaled to break positive definiteness) leaves exactly its rows zero.
+    n = 260
+    va = _problem(n, m, 2, cond_yz, stream=70 + m)
+    prep = va["U_prep"]
+    locs = va["locsord"]
+    N = locs.shape[0]
+    D = np.sqrt(((locs[:, None, :] - locs[None, :, :]) ** 2).sum(-1))
+    covVals = O.MaternFun(D, np.array([1.2, 0.25, 1.5])) + 0.05 * np.eye(N)
+    nobs = int(va["obs"].sum())
+    tau = H.make_nuggets(nobs, stream=70)
+    with G.UHandle(locs, prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+        got = h.U_NZentries_mat(covVals, tau)
+        ref = O.U_NZentries_mat(nobs, prep["revNNarray"], covVals, tau)
+        assert got["nfail"] == ref["nfail"] == 0
+        assert np.array_equal(got["Lentries"] == 0, ref["Lentries"] == 0)
+        assert _rowscaled_err(got["Lentries"], ref["Lentries"]) < VAL_TOL
+        assert np.array_equal(got["Zentries"], ref["Zentries"])
+        packed, _, _ = h.values_packed_mat(covVals, tau)
+        not_na = (prep["revNNarray"][:, ::-1] != 0).ravel() & (prep["revNNarray"][:, ::-1] != NA_I32).ravel()
+        assert np.array_equal(packed, np.concatenate([got["Lentries"].ravel()[not_na], got["Zentries"]]))
+        bad = covVals.copy()
+        bad[N - 3, N - 3] = -1.0
+        g2, r2 = h.U_NZentries_mat(bad, tau), O.U_NZentries_mat(nobs, prep["revNNarray"], bad, tau)
+        assert g2["nfail"] == r2["nfail"] > 0
+        assert np.array_equal(np.all(g2["Lentries"] == 0, axis=1), np.all(r2["Lentries"] == 0, axis=1))
+    # through createU: same sparse matrix as the triplet assembly of the restated values
+    if cond_yz != "zy":
+        Ug = G.createU(va, [1.2, 0.25, 1.5], tau, covmodel=covVals)["U"].tocsc()
+        Ug.sort_indices()
+        import scipy.sparse as sp
+        want = np.concatenate([ref["Lentries"].ravel()[not_na], ref["Zentries"]])
+        Uo = sp.coo_matrix((want, (prep["colindices"] - 1, prep["rowpointers"] - 1)), shape=Ug.shape).tocsc()
+        Uo.sort_indices()
+        assert np.array_equal(Ug.indptr, Uo.indptr) and np.array_equal(Ug.indices, Uo.indices)
+        colmax = np.maximum.reduceat(np.abs(Uo.data), Uo.indptr[:-1])
+        assert (np.abs(Ug.data - Uo.data) / np.repeat(colmax, np.diff(Uo.indptr))).max() < VAL_TOL
 
 
 def test_zero_nugget_createU_trimming():
