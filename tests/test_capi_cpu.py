@@ -48,6 +48,28 @@ def test_bad_arguments_are_status_codes_not_crashes():
     assert st == _lib.GPV_ERR_ARG
     assert G.lib.gpv_packed_len(None) == 0
     G.lib.gpv_destroy(None)
+    # the entry points added for SURVEY.md 8(f): null handles / arrays are status codes too
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    assert G.lib.gpv_csc_dims(None, C.byref(a), C.byref(b), C.byref(c)) == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_u_sparsity(None, None, None) == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_u_csc_pattern(None, None, None) == _lib.GPV_ERR_ARG
+    nf, ff = C.c_int64(0), C.c_int64(0)
+    assert G.lib.gpv_u_values_csc(None, b"matern", None, 3, None, None, 0, None, C.byref(nf), C.byref(ff)) == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_u_nzentries_mat(None, None, None, 0, None, None, C.byref(nf), C.byref(ff)) == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_multi_csc_dims(None, C.byref(a), C.byref(b), C.byref(c)) == _lib.GPV_ERR_ARG
+    assert G.lib.gpv_whichCondOnLatent(None, 5, 3, 0, None) == _lib.GPV_ERR_ARG
+
+
+def test_whichCondOnLatent_is_host_code_and_needs_no_device():
+    # 4 locations, m = 2: row k conditions on latent y only for the best earlier neighbour and its own
+    # latent neighbours (R/whichCondOnLatent.R:2-27); NA stays NA, self is always TRUE
+    NA = np.iinfo(np.int32).min
+    NN = np.asfortranarray(np.array([[1, NA, NA], [2, 1, NA], [3, 2, 1], [4, 3, 2]], dtype=np.int32))
+    out = np.empty_like(NN)
+    assert G.lib.gpv_whichCondOnLatent(NN.ctypes.data, 4, 3, 0, out.ctypes.data) == _lib.GPV_OK
+    assert out[0, 0] == 1 and out[0, 1] == NA and out[0, 2] == NA
+    assert np.all(out[:, 0] == 1) and out[1, 2] == NA
+    assert set(np.unique(out[2:, 1:])) <= {0, 1}
 
 
 def test_unknown_covtype_is_an_error_before_touching_the_device():
