@@ -434,6 +434,22 @@ def main():
         if wl["layout"] == "z":
             extras["loglik_value"] = -0.5 * (ldn - ldd + qn - qd + n_total * float(np.log(2 * np.pi)))
         if wl["layout"] == "z":
+            # estimation loop: data and nuggets resident on the handle, only covparms go up (gpv_loglik_z
+            # with NULL vectors), 6 doubles come back
+            try:
+                h.loglik_z(covType, covparms, nug_np, tau_np, z)
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(ll_steps):
+                    r_res = h.loglik_z(covType, covparms, None, None, None)
+                barrier()
+                t_res = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+                extras["loglik_e2e_resident_evals_per_s"] = ll_steps / float(t_res.item())
+            except G.GpvError:
+                pass
+        if wl["layout"] == "z":
             # end-to-end likelihood call with host buffers (nuggets, tau, z up; 6 doubles back)
             host_z = torch.from_numpy(z).pin_memory().numpy()
             for _ in range(2):

@@ -20,7 +20,7 @@ EXPORTED = [
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
     "gpv_u_nzentries_mat", "gpv_u_values_packed_mat", "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
     "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
-    "gpv_loglik_numerator", "gpv_loglik_z", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
+    "gpv_loglik_numerator", "gpv_loglik_z", "gpv_set_scalar_nugget", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn", "gpv_whichCondOnLatent",
     "gpv_multi_create", "gpv_multi_destroy", "gpv_multi_num_devices", "gpv_multi_packed_len",
@@ -83,6 +83,8 @@ def _load():
     L.gpv_u_nzentries_mat.restype = i32
     L.gpv_u_values_packed_mat.argtypes = [vp, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]
     L.gpv_u_values_packed_mat.restype = i32
+    L.gpv_set_scalar_nugget.argtypes = [vp, C.c_double]
+    L.gpv_set_scalar_nugget.restype = i32
     L.gpv_loglik_numerator.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i64, i32, vp]
     L.gpv_loglik_numerator.restype = i32
     L.gpv_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, i32, vp]

@@ -150,6 +150,14 @@ __global__ void expand_z_kernel(const double* __restrict__ zord, const int32_t* 
   const int r = obsrank[i];
   zloc[i] = r >= 0 ? zord[r] : 0.0;
 }
+// nuggets.all.ord / nuggets.ord of a scalar nugget (createU.R:70-78): the nugget at observed locations,
+// 0 at the others
+__global__ void fill_scalar_nugget_kernel(const int32_t* __restrict__ obsrank, int64_t Nlocs, int64_t n, double v,
+                                          double* __restrict__ nuggets, double* __restrict__ tau) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Nlocs) nuggets[i] = obsrank[i] >= 0 ? v : 0.0;
+  if (i < n) tau[i] = v;
+}
 // pure `z` conditioning: every non-missing neighbour is conditioned on the response, only self on
 // the latent (vecchia_specify.R:189-190) -> the row's mask is exactly the self bit
 __global__ void check_pure_z_kernel(const uint64_t* __restrict__ cond, int64_t nrows, int p,
@@ -402,6 +410,7 @@ struct gpv_handle {
   // compressed-column output (gpv_csc.inc), built on first use
   bool csc_ready = false;
   bool cond_uploaded = false;         // the create-time revCond is on the device
+  bool nug_resident = false, z_resident = false;   // d_nuggets + d_tau / d_zord hold what the last likelihood call used
   uint8_t* d_csc_rank = nullptr;      // [nrows][p] place of each compacted entry inside its column
   uint64_t* d_csc_cond = nullptr;     // [nrows] the revCond mask the structure was built from
   int64_t csc_len = 0, csc_ncols = 0;
@@ -1033,6 +1042,7 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   CovSetup cs;
   gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
+  h->nug_resident = false;             // d_nuggets is shared with the likelihood calls
   CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
   const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
@@ -1104,18 +1114,31 @@ extern "C" gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, co
 static gpv_status loglik_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
                                 const double* nuggets, const double* nuggets_obsord, const double* zord,
                                 int64_t n, int64_t skip_rows, int include_obs_terms, double out5[5]) {
-  if (!h || !nuggets || !nuggets_obsord || !zord || !out5) return fail(GPV_ERR_ARG, "likelihood: null argument");
+  if (!h || !out5) return fail(GPV_ERR_ARG, "likelihood: null argument");
+  if ((nuggets == nullptr) != (nuggets_obsord == nullptr)) return fail(GPV_ERR_ARG, "likelihood: give both nugget vectors or neither");
   if (!h->have_obs) return fail(GPV_ERR_ARG, "likelihood: handle was created without obs");
   if (n != h->n_obs) return fail(GPV_ERR_ARG, "likelihood: n=%lld but sum(obs)=%lld", (long long)n, (long long)h->n_obs);
+  // NULL vectors reuse what is resident from the previous call / gpv_set_scalar_nugget: in the estimation
+  // loop (R/vecchia_wrappers.R:72-93) z never changes and the nugget is one scalar parameter
+  if (!nuggets && !h->nug_resident) return fail(GPV_ERR_ARG, "likelihood: no nuggets given and none resident on the handle");
+  if (!zord && !h->z_resident) return fail(GPV_ERR_ARG, "likelihood: no data given and none resident on the handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CovSetup cs;
   gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
   s = ensure(&h->d_tau, (size_t)n); if (s) return s;
   s = ensure(&h->d_zord, (size_t)n); if (s) return s;
-  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_zord, zord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  if (nuggets) {
+    h->nug_resident = false;
+    CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->nug_resident = true;
+  }
+  if (zord) {
+    h->z_resident = false;
+    CUDA_TRY(cudaMemcpyAsync(h->d_zord, zord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    h->z_resident = true;
+  }
   int nblocks = 0;
   if (h->nrows > 0) {
     s = launch_sets(h, &cs, h->d_nuggets, nullptr, 0, h->d_zord, skip_rows, true, h->stream, &nblocks);
@@ -1136,6 +1159,19 @@ static gpv_status loglik_common(gpv_handle* h, const char* covType, const double
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out5, h->d_loglik, sizeof(double) * 5, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GPV_OK;
+}
+
+extern "C" gpv_status gpv_set_scalar_nugget(gpv_handle* h, double nugget) {
+  if (!h) return fail(GPV_ERR_ARG, "gpv_set_scalar_nugget: null handle");
+  if (!h->have_obs) return fail(GPV_ERR_ARG, "gpv_set_scalar_nugget: handle was created without obs");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gpv_status s = ensure(&h->d_tau, (size_t)(h->n_obs ? h->n_obs : 1)); if (s) return s;
+  const int64_t m = h->Nlocs > h->n_obs ? h->Nlocs : h->n_obs;
+  fill_scalar_nugget_kernel<<<grid_for(m, 256), 256, 0, h->stream>>>(h->d_obsrank, h->Nlocs, h->n_obs, nugget, h->d_nuggets, h->d_tau);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  h->nug_resident = true;
   return GPV_OK;
 }
 

@@ -222,29 +222,35 @@ class UHandle:
                                    _ptr(out), C.byref(nfail), C.byref(first)))
         return out, int(nfail.value), int(first.value)
 
+    def set_scalar_nugget(self, nugget):
+        """nuggets.all.ord / nuggets.ord of a scalar nugget, built on the device (createU.R:70-78); the
+        likelihood calls then take nuggets=None."""
+        check(lib.gpv_set_scalar_nugget(self._h, float(nugget)))
+
     def loglik_numerator(self, covType, covparms, nuggets, nuggets_obsord, zord, skip_rows=0,
                          include_obs_terms=-1):
-        """(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, fused on the GPU."""
+        """(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, fused on the GPU.  None for the
+        nuggets / for zord reuses what is resident on the handle (estimation loop)."""
         cov = _f64(covparms)
-        nug = _f64(nuggets)
-        tau = _f64(nuggets_obsord)
-        z = _f64(zord)
+        nug = None if nuggets is None else _f64(nuggets)
+        tau = None if nuggets_obsord is None else _f64(nuggets_obsord)
+        z = None if zord is None else _f64(zord)
         out = np.zeros(3, dtype=np.float64)
         check(lib.gpv_loglik_numerator(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug),
-                                       _ptr(tau), _ptr(z), tau.size, int(skip_rows),
+                                       _ptr(tau), _ptr(z), self.n_obs, int(skip_rows),
                                        int(include_obs_terms), _ptr(out)))
         return float(out[0]), float(out[1]), int(out[2])
 
     def loglik_z(self, covType, covparms, nuggets, nuggets_obsord, zord, include_obs_terms=-1):
         """Whole log-likelihood for pure `z` conditioning (gpv_loglik_z): dict(loglik, quadform_num,
-        logdet_num, quadform_denom, logdet_denom, nfail)."""
+        logdet_num, quadform_denom, logdet_denom, nfail).  None arguments reuse resident data."""
         cov = _f64(covparms)
-        nug = _f64(nuggets)
-        tau = _f64(nuggets_obsord)
-        z = _f64(zord)
+        nug = None if nuggets is None else _f64(nuggets)
+        tau = None if nuggets_obsord is None else _f64(nuggets_obsord)
+        z = None if zord is None else _f64(zord)
         out = np.zeros(6, dtype=np.float64)
         check(lib.gpv_loglik_z(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau), _ptr(z),
-                               tau.size, int(include_obs_terms), _ptr(out)))
+                               self.n_obs, int(include_obs_terms), _ptr(out)))
         return dict(loglik=float(out[0]), quadform_num=float(out[1]), logdet_num=float(out[2]),
                     quadform_denom=float(out[3]), logdet_denom=float(out[4]), nfail=int(out[5]))
 

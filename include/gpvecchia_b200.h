@@ -152,6 +152,14 @@ gpv_status gpv_loglik_z(gpv_handle* h, const char* covType, const double* covpar
                         const double* nuggets, const double* nuggets_obsord, const double* zord,
                         int64_t n, int include_obs_terms, double out[6]);
 
+/* Data residency for the estimation loop (vecchia_estimate, R/vecchia_wrappers.R:72-93: z is fixed and the
+ * nugget is one scalar parameter).  In gpv_loglik_numerator / gpv_loglik_z, zord == NULL reuses the data of
+ * the previous likelihood call on the handle, and nuggets == nuggets_obsord == NULL reuses its nuggets or
+ * those of gpv_set_scalar_nugget, which builds nuggets.all.ord / nuggets.ord of a scalar nugget on the
+ * device (createU.R:70-78: the nugget at observed locations, 0 elsewhere).  A call then moves ~30 bytes
+ * each way.  GPV_ERR_ARG if nothing is resident; any U-values call on the handle drops the nuggets. */
+gpv_status gpv_set_scalar_nugget(gpv_handle* h, double nugget);
+
 /* ---- device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`) ------
  * d_nuggets[Nlocs] device pointer.  d_out: row-major (rows x p) when packed == 0, packed order
  * otherwise.  stream: a cudaStream_t cast to void* (NULL = the handle's own stream).

@@ -116,6 +116,9 @@ SEXP gpvb200_create(SEXP locsord, SEXP revNNarray, SEXP revCond, SEXP obs) {
                    LOGICAL(ob), 0, N, device_from_option()));
   SEXP ptr = PROTECT(R_MakeExternalPtr(h, Rf_install("gpv_handle"), R_NilValue));
   R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  double nobs = 0;                                            /* for likelihood calls that pass zord = NULL */
+  for (R_xlen_t i = 0; i < XLENGTH(ob); ++i) nobs += (LOGICAL(ob)[i] == TRUE);
+  Rf_setAttrib(ptr, Rf_install("n_obs"), Rf_ScalarReal(nobs));
   UNPROTECT(3);
   return ptr;
 }
@@ -186,13 +189,21 @@ SEXP gpvb200_U_sparsity(SEXP ptr) {
   return out;
 }
 
+/* scalar nugget built on the device; afterwards the likelihood calls may pass NULL (R: NULL) vectors */
+SEXP gpvb200_set_scalar_nugget(SEXP ptr, SEXP nugget) {
+  check(gpv_set_scalar_nugget(get_handle(ptr), Rf_asReal(nugget)));
+  return R_NilValue;
+}
+
 /* c(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, no U materialisation */
 SEXP gpvb200_loglik_numerator(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord,
                               SEXP nuggets_ord, SEXP zord, SEXP skip_rows) {
   gpv_handle* h = get_handle(ptr);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
   check(gpv_loglik_numerator(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                             REAL(nuggets_all_ord), REAL(nuggets_ord), REAL(zord), XLENGTH(zord),
+                             Rf_isNull(nuggets_all_ord) ? NULL : REAL(nuggets_all_ord),
+                             Rf_isNull(nuggets_ord) ? NULL : REAL(nuggets_ord), Rf_isNull(zord) ? NULL : REAL(zord),
+                             Rf_isNull(zord) ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(zord),
                              (int64_t)Rf_asReal(skip_rows), -1, REAL(out)));
   UNPROTECT(1);
   return out;
@@ -215,6 +226,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_b200_csc_pattern", (DL_FUNC)&gpvb200_csc_pattern, 1},
     {"_GPvecchia_b200_U_values_csc", (DL_FUNC)&gpvb200_U_values_csc, 5},
     {"_GPvecchia_b200_U_sparsity", (DL_FUNC)&gpvb200_U_sparsity, 1},
+    {"_GPvecchia_b200_set_scalar_nugget", (DL_FUNC)&gpvb200_set_scalar_nugget, 2},
     {"_GPvecchia_b200_loglik_numerator", (DL_FUNC)&gpvb200_loglik_numerator, 7},
     {"_GPvecchia_b200_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},
     {NULL, NULL, 0}};

@@ -335,6 +335,40 @@ def test_covmodel_matrix_branch(m, cond_yz):
         assert (np.abs(Ug.data - Uo.data) / np.repeat(colmax, np.diff(Uo.indptr))).max() < VAL_TOL
 
 
+def test_likelihood_reuses_resident_data_and_scalar_nugget():
+    # estimation loop (R/vecchia_wrappers.R:72-93): z fixed, nugget one scalar -> None arguments reuse what
+    # is resident on the handle; gpv_set_scalar_nugget builds nuggets.all.ord / nuggets.ord on the device
+    n, m = 3000, 15
+    for cond_yz in ("z", "zy"):
+        va = _problem(n, m, 2, cond_yz, stream=80)
+        prep = va["U_prep"]
+        N = va["locsord"].shape[0]
+        z = H.make_data(n, stream=80)
+        nug_all = np.concatenate([np.full(n, 0.07), np.zeros(N - n)])
+        tau = np.full(n, 0.07)
+        skip = n if cond_yz == "zy" else 0
+        with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+            with pytest.raises(G.GpvError):
+                h.loglik_numerator("matern", [1.0, 0.1, 1.5], None, None, None, skip_rows=skip)
+            want = [h.loglik_numerator("matern", [1.0, r, 1.5], nug_all, tau, z, skip_rows=skip) for r in (0.1, 0.2)]
+            got = [h.loglik_numerator("matern", [1.0, r, 1.5], None, None, None, skip_rows=skip) for r in (0.1, 0.2)]
+            assert got == want                                   # same kernel, same device data: bit-identical
+            h.set_scalar_nugget(0.07)
+            assert h.loglik_numerator("matern", [1.0, 0.2, 1.5], None, None, None, skip_rows=skip) == want[1]
+            h.set_scalar_nugget(0.11)
+            a = h.loglik_numerator("matern", [1.0, 0.2, 1.5], None, None, None, skip_rows=skip)
+            b = h.loglik_numerator("matern", [1.0, 0.2, 1.5], nug_all / 0.07 * 0.11, tau / 0.07 * 0.11, z, skip_rows=skip)
+            assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-12 * abs(b[1])
+            if cond_yz == "z":
+                r1 = h.loglik_z("matern", [1.0, 0.2, 1.5], None, None, None)
+                r2 = h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all / 0.07 * 0.11, tau / 0.07 * 0.11, z)
+                assert abs(r1["loglik"] - r2["loglik"]) <= 1e-12 * abs(r2["loglik"])
+            # a U-values call overwrites the nugget buffer: the next reuse must be refused, not silently wrong
+            h.values_packed("matern", [1.0, 0.2, 1.5], nug_all, tau)
+            with pytest.raises(G.GpvError):
+                h.loglik_numerator("matern", [1.0, 0.2, 1.5], None, None, None, skip_rows=skip)
+
+
 def test_zero_nugget_createU_trimming():
     n, m = 300, 6
     va = _problem(n, m, 2, "SGV", stream=51)
