@@ -135,7 +135,9 @@ def make_inputs(wl, n_total, world, rank, device, use_gpu_nn=True):
     z = H.make_data(n_total, stream=2)
     if wl["layout"] == "z":
         # 'z' conditioning: neighbours on the response, self on the latent (vecchia_specify.R:189-190)
-        cuts = shard.uniform_cuts(n_total, world)
+        # equal expected kernel time per rank (late rows gather from more than the L2 holds); the closed
+        # forms feel it twice as much, relatively, as the slower general-nu kernel
+        cuts = shard.locality_cuts(n_total, world, d, penalty_scale=1.0 if wl["tag"] != "general" else 0.5)
         rb, re_ = int(cuts[rank]), int(cuts[rank + 1])
         if use_gpu_nn:
             revNN = H.ordered_nn_gpu(locs_obs, m, rb, re_, device=device)
@@ -229,12 +231,13 @@ def main():
     p = m + 1
     cov_desc = f"Matern nu={wl['nu']}" if wl["covType"] == "matern" else "esqe"
     workload = (f"{args.workload}: createU/U_NZentries, n={n_total} uniform {d}-D locs"
-                f"{' (' + str(wl['n']) + '/GPU)' if wl['scaling'] == 'weak' else ''}"
+                f"{' (' + str(wl['n']) + '/GPU on average)' if wl['scaling'] == 'weak' else ''}"
                 f"{' + ' + str(wl['n_pred']) + ' prediction locs' if wl['n_pred'] else ''}, m={m}, {cov_desc}, "
                 f"'{wl['layout']}' conditioning")
     per_row_mb = (p * 4 + p * 8) / 1e6
     config = dict(workload=workload, n=n_total, m=m, d=d, covmodel=wl["covType"], nu=wl["nu"], cond_yz=wl["layout"],
-                  sharding=f"rows by contiguous range over {world} rank(s); locs and nuggets replicated",
+                  sharding=(f"rows by contiguous range over {world} rank(s), cut for equal expected kernel time "
+                            "(late rows gather from more than the L2 holds: gpvecchia_b200/shard.py); locs and nuggets replicated"),
                   l2=(f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank "
                       + ("(larger than the 126 MB L2)" if per_row_mb * n_total / world > 126 else
                          "(fits the 126 MB L2: this workload is launch-latency bound, not a bandwidth case)")))

@@ -101,3 +101,17 @@ def test_native_whichCondOnLatent_scales():
     assert np.all(C_[:, 0] == 1) and np.array_equal(C_ == -1, NN == 0)
     frac = (C_[m + 1:, 1:] == 1).mean()
     assert 0.05 < frac < 0.95          # SGV conditions on a mix of y and z
+
+
+def test_locality_cuts_balance_expected_cost():
+    # equal sums of the measured locality weight per rank; one rank = everything; small problems = uniform
+    for world in (1, 2, 4, 8):
+        n = world * 1_000_000
+        cuts = shard.locality_cuts(n, world, 2)
+        assert cuts[0] == 0 and cuts[-1] == n and np.all(np.diff(cuts) > 0) and cuts.size == world + 1
+        w = shard.locality_weight(np.arange(n), 24)
+        cost = np.add.reduceat(w, cuts[:-1])
+        assert cost.max() / cost.min() < 1.0001
+        if world > 1:
+            assert np.diff(cuts)[0] > np.diff(cuts)[-1]          # early rows are cheaper: rank 0 takes more
+    assert np.array_equal(shard.locality_cuts(40_000, 4, 2), shard.uniform_cuts(40_000, 4))
