@@ -90,12 +90,19 @@ constexpr int kSolveBlock = GPV_SOLVE_BLOCK;   // rows per shuffle round of the 
 // Polynomial / reduction constants live in constant memory so DFMA takes them as c[bank][offset]
 // operands; as literals ptxas re-materialised them with two UMOVs each inside the pair loop
 // (8% of all issued instructions in the first profile, profiles/r01_*).
-__constant__ double kMathC[8] = {
+__constant__ double kMathC[10] = {
     GPV_EXP_Q0, GPV_EXP_Q1, GPV_EXP_Q2, GPV_EXP_Q3,
     GPV_EXP_64_OVER_LN2,           // [4]
     -GPV_EXP_LN2_64_HI,            // [5]
     -GPV_EXP_LN2_64_LO,            // [6]
-    1.0e-300};                     // [7] sqrt guard
+    1.0e-300,                      // [7] sqrt guard
+    -GPV_EXP_LN2_64,               // [8] one-FMA reduction of the pair stage (exp_negarg_fast_n)
+    0.0};
+// GPV_PAIR_FAST = 1: the closed-form pair stage uses the shorter sqrt / exp sequences below
+// (neg_sqrt_fast_n, exp_negarg_fast_n): 21 instead of 26 fp64 instructions per Matern-1.5 pair.
+#ifndef GPV_PAIR_FAST
+#define GPV_PAIR_FAST 1
+#endif
 __constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to shared memory per block
 
 #ifndef GPV_MINB21
@@ -258,16 +265,78 @@ __device__ __forceinline__ void exp_negarg_n(const double (&ns_in)[N], double (&
   for (int i = 0; i < N; ++i)
     out[i] = __hiloint2double(__double2hiint(v[i]) + (n[i] >> 6) * 1048576, __double2loint(v[i]));
 }
+// The pair stage's own sqrt and exp (GPV_PAIR_FAST).  The kernel is bound by the fp64 pipe and 56 % of
+// its fp64 instructions are these two functions (profiles/r01_u_band_closed_*), so they are cut to what
+// the parity bar needs -- about one ulp of the ARGUMENT, which is what the reference's own
+// sqrt -> divide -> multiply chain carries (Matern.cpp:38-68):
+//  * -sqrt(w) = g (1 + e/2 + 3 e^2/8), g = -w y0, e = 1 - w y0^2 from the MUFU.RSQ64H seed y0
+//    (|e| < 2^-18.9: the dropped term 5 e^3/16 is below 2^-58).  The rounding error d of g enters e
+//    with the opposite sign, so half of it cancels: 5 fp64 instructions instead of the 9 of
+//    sqrt_pos_n, and a dependency chain of 4 instead of 7.
+//  * exp: r = ns - kf c in ONE fma with c = nearest(ln2/64); the product is exact inside the fma, what is
+//    lost is kf (ln2/64 - c) <= |ns| 2^-53, i.e. half an ulp of the argument (absolute error of the
+//    result <= s e^-s 2^-53 <= 0.37 ulp(1)).  2 instead of 3 instructions; polynomial as before.
+// Verified on the host against mpmath over the seed-error envelope: tools/check_pair_fast.py.
+template <int N>
+__device__ __forceinline__ void neg_sqrt_fast_n(const double (&w)[N], double (&out)[N]) {
+  double y0[N], g[N], e[N], a[N], ge[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) y0[i] = rsqrt_seed(w[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = w[i] * (-y0[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(g[i], y0[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { a[i] = fma(e[i], 0.375, 0.5); ge[i] = g[i] * e[i]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(a[i], ge[i], g[i]);
+}
+template <int N>
+__device__ __forceinline__ void exp_negarg_fast_n(const double (&ns_in)[N], double (&out)[N],
+                                                  const double* __restrict__ etab) {
+  const double kShift = 6755399441055744.0;
+  double ns[N], t[N], kf[N], r[N], T[N], r2[N], qq[N], p[N], v[N];
+  int n[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)   // clamp at -700 on the integer pipe, see exp_negarg_n
+    ns[i] = __hiloint2double((int)min((unsigned)__double2hiint(ns_in[i]), 0xC085E000u), __double2loint(ns_in[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fma(ns[i], kMathC[4], kShift);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { kf[i] = t[i] - kShift; n[i] = __double2loint(t[i]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r[i] = fma(kf[i], kMathC[8], ns[i]); T[i] = etab[n[i] & 63]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; qq[i] = fma(kMathC[3], r[i], kMathC[2]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) qq[i] = fma(qq[i], r[i], kMathC[1]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) qq[i] = fma(qq[i], r[i], kMathC[0]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(qq[i], r2[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = fma(T[i], p[i], T[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    out[i] = __hiloint2double(__double2hiint(v[i]) + (n[i] >> 6) * 1048576, __double2loint(v[i]));
+}
 struct CovConsts { double c0, c1, c2, c3, c4; };   // what the closed forms read of UParams, by value
 template <int KIND, int N, class C>
 __device__ __forceinline__ void cov_eval_n(const double (&r2)[N], double (&v)[N], const C& q,
                                            const double* __restrict__ etab) {
   static_assert(KIND != COV_GENERAL, "closed forms only");
   double sq[N], ns[N], e[N];
+#if GPV_PAIR_FAST
+  neg_sqrt_fast_n<N>(r2, sq);
+#pragma unroll
+  for (int i = 0; i < N; ++i) ns[i] = sq[i] * q.c1;
+  exp_negarg_fast_n<N>(ns, e, etab);
+#else
   sqrt_pos_n<N>(r2, sq);
 #pragma unroll
   for (int i = 0; i < N; ++i) ns[i] = sq[i] * (-q.c1);
   exp_negarg_n<N>(ns, e, etab);
+#endif
   if (KIND == COV_EXP) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = q.c0 * e[i];
@@ -276,12 +345,20 @@ __device__ __forceinline__ void cov_eval_n(const double (&r2)[N], double (&v)[N]
     for (int i = 0; i < N; ++i) v[i] = fma(-q.c0, ns[i], q.c0) * e[i];
   } else if (KIND == COV_M25) {
 #pragma unroll
+#if GPV_PAIR_FAST
+    for (int i = 0; i < N; ++i) v[i] = e[i] * fma(ns[i], fma(ns[i], q.c0 * (1.0 / 3.0), -q.c0), q.c0);   // c0/3: loop invariant
+#else
     for (int i = 0; i < N; ++i) v[i] = q.c0 * e[i] * fma(ns[i], fma(ns[i], 1.0 / 3.0, -1.0), 1.0);
+#endif
   } else {
     double ns2[N], e2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) ns2[i] = r2[i] * (-q.c3);
+#if GPV_PAIR_FAST
+    exp_negarg_fast_n<N>(ns2, e2, etab);
+#else
     exp_negarg_n<N>(ns2, e2, etab);
+#endif
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fma(q.c2, e2[i], q.c4 * e[i]);
   }
