@@ -5,8 +5,9 @@ the host-side mirror of the reference's R interface for that path.  Importing fa
 the library has not been built: there is no CPU fallback."""
 from ._lib import lib, GpvError, LIB_PATH
 from .host import (UHandle, MultiHandle, U_NZentries, MaternFun, EsqeFun, U_sparsity, createU,
-                   vecchia_likelihood, vecchia_likelihood_U, vecchia_loglik_numerator)
+                   vecchia_likelihood, vecchia_likelihood_U, vecchia_loglik_numerator,
+                   ic0, createUcpp, createUcppM)
 
 __all__ = ["lib", "GpvError", "LIB_PATH", "UHandle", "MultiHandle", "U_NZentries", "MaternFun", "EsqeFun",
            "U_sparsity", "createU", "vecchia_likelihood", "vecchia_likelihood_U",
-           "vecchia_loglik_numerator"]
+           "vecchia_loglik_numerator", "ic0", "createUcpp", "createUcppM"]

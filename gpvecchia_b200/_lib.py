@@ -23,6 +23,7 @@ EXPORTED = [
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_set_scalar_nugget", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
     "gpv_launch_count", "gpv_U_NZentries", "gpv_MaternFun", "gpv_EsqeFun",
     "gpv_measure_fp64_peak", "gpv_measure_copy_bw", "gpv_harness_ordered_nn", "gpv_whichCondOnLatent",
+    "gpv_ic0", "gpv_createUcppM", "gpv_createUcpp",
     "gpv_multi_create", "gpv_multi_destroy", "gpv_multi_num_devices", "gpv_multi_packed_len",
     "gpv_multi_row_cuts", "gpv_multi_set_revcond", "gpv_multi_u_values_packed",
     "gpv_multi_loglik_numerator", "gpv_multi_loglik_z", "gpv_set_last_error",
@@ -79,6 +80,12 @@ def _load():
     L.gpv_multi_u_values_csc.restype = i32
     L.gpv_whichCondOnLatent.argtypes = [vp, i64, i32, i64, vp]
     L.gpv_whichCondOnLatent.restype = i32
+    L.gpv_ic0.argtypes = [i64, vp, vp, i64, vp]
+    L.gpv_ic0.restype = i32
+    L.gpv_createUcppM.argtypes = [i64, vp, vp, i64, vp]
+    L.gpv_createUcppM.restype = i32
+    L.gpv_createUcpp.argtypes = [i64, i32, vp, vp, i64, vp, vp, vp, i32]
+    L.gpv_createUcpp.restype = i32
     L.gpv_u_nzentries_mat.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64)]
     L.gpv_u_nzentries_mat.restype = i32
     L.gpv_u_values_packed_mat.argtypes = [vp, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]

@@ -1363,3 +1363,4 @@ extern "C" double gpv_selftest_table_eval_host(double w, double sig2, double ran
 
 #include "gpv_csc.inc"
 #include "gpv_mat.inc"
+#include "gpv_ic0.inc"

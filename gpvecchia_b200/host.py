@@ -421,6 +421,47 @@ def EsqeFun(distmat, covparms, device=0):
 
 
 # --------------------------------------------------------------------------------------------------
+# ic0 / createUcppM / createUcpp (R/RcppExports.R:53-63): the incomplete-Cholesky branch of createU
+# --------------------------------------------------------------------------------------------------
+def ic0(ptrs, inds, vals):
+    """Incomplete Cholesky on a fixed pattern (src/ic0.cpp:43-63): ptrs (N+1), inds and vals as R numeric
+    vectors, 0-based.  Returns the new values; a float64 array passed as `vals` is overwritten in place,
+    as the reference overwrites its argument."""
+    ptrs, inds = _f64(ptrs), _f64(inds)
+    out = vals if (isinstance(vals, np.ndarray) and vals.dtype == np.float64 and vals.flags.c_contiguous) else _f64(vals).copy()
+    if out.size != inds.size:
+        raise ValueError("vals and inds differ in length")
+    check(lib.gpv_ic0(ptrs.size - 1, _ptr(ptrs), _ptr(inds), inds.size, _ptr(out)))
+    return out
+
+
+def createUcppM(ptrs, inds, cov_vals):
+    """src/ic0.cpp:68-71: ic0 on covariances the caller evaluated (matrix or function covmodel)."""
+    ptrs, inds = _f64(ptrs), _f64(inds)
+    out = cov_vals if (isinstance(cov_vals, np.ndarray) and cov_vals.dtype == np.float64 and cov_vals.flags.c_contiguous) else _f64(cov_vals).copy()
+    if out.size != inds.size:
+        raise ValueError("cov_vals and inds differ in length")
+    check(lib.gpv_createUcppM(ptrs.size - 1, _ptr(ptrs), _ptr(inds), inds.size, _ptr(out)))
+    return out
+
+
+def createUcpp(ptrs, inds, locsord, covparams, device=0):
+    """src/ic0.cpp:77-92: Matern covariance of every stored (row, column) pair on the device, then ic0."""
+    ptrs, inds = _f64(ptrs), _f64(inds)
+    locs = np.asarray(locsord, dtype=np.float64)
+    if locs.ndim != 2 or locs.shape[0] != ptrs.size - 1:
+        raise ValueError("locsord must have one row per pattern row")
+    cov = _f64(covparams)
+    if cov.size != 3:
+        raise ValueError("covparams = c(sig2, range, smooth)")
+    lc = _colmajor(locs, np.float64)
+    out = np.zeros(inds.size, dtype=np.float64)
+    check(lib.gpv_createUcpp(locs.shape[0], locs.shape[1], _ptr(ptrs), _ptr(inds), inds.size, _ptr(lc),
+                             _ptr(cov), _ptr(out), int(device)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # U_sparsity, vectorised (R/U_sparsity.R:5-81 is an interpreter loop over all locations)
 # --------------------------------------------------------------------------------------------------
 def U_sparsity(locs, NNarray, obs, Cond):

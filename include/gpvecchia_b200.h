@@ -240,6 +240,23 @@ gpv_status gpv_EsqeFun(const double* dist, int64_t len, const double* covparms, 
 gpv_status gpv_measure_fp64_peak(int device, double* tflops);
 gpv_status gpv_measure_copy_bw(int device, double* gbs);
 
+/* ---- ic0 / createUcppM / createUcpp (src/ic0.cpp:43-63, :68-71, :77-92; R/RcppExports.R:53-63) -------
+ * The incomplete-Cholesky (MRA) branch of createU (R/createU.R:89-106).  The pattern is compressed sparse
+ * row, lower triangular, every row ending on its diagonal: ptrs (N + 1) and inds (nnz) are R numeric
+ * vectors holding 0-based integers, exactly what createU.R:90-91 builds.  gpv_ic0 overwrites vals (nnz)
+ * with the incomplete-Cholesky values, like the reference (which modifies its argument in place and
+ * returns it); gpv_createUcppM is the same call under the name createU uses for a matrix or function
+ * covmodel.  gpv_createUcpp first fills vals with MaternFun(|locsord[i,] - locsord[inds[j],]|, covparams)
+ * for every stored entry -- on `device`, one thread per entry -- and then runs ic0 on the host (row i reads
+ * the finished rows of its columns: a sequential sweep, as in the reference).  locsord: N x d column-major.
+ * Unlike the reference (which prints "ERROR" and carries on, :57-58) an entry right of the diagonal, a
+ * non-integer or out-of-range index, or a column whose own row is empty is GPV_ERR_ARG and vals is left
+ * untouched. */
+gpv_status gpv_ic0(int64_t N, const double* ptrs, const double* inds, int64_t nnz, double* vals);
+gpv_status gpv_createUcppM(int64_t N, const double* ptrs, const double* inds, int64_t nnz, double* cov_vals);
+gpv_status gpv_createUcpp(int64_t N, int d, const double* ptrs, const double* inds, int64_t nnz,
+                          const double* locsord, const double* covparams, double* vals, int device);
+
 /* ---- whichCondOnLatent (R/whichCondOnLatent.R:2-27), host code -------------------------------
  * The sparse-general-Vecchia rule (vecchia_specify.R:183-185): NNarray is the un-reversed n x p neighbour
  * array, column-major, 1-based, missing = NA_integer_ (or 0); firstind_pred <= 0 means n + 1.

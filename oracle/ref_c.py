@@ -54,6 +54,10 @@ def lib():
     L.gpv_oracle_block_cond_proxy.argtypes = [C.c_long, C.c_long, C.c_int, C.c_int, dp, ip, dp, dp,
                                               C.c_char_p, dp]
     L.gpv_oracle_block_cond_proxy.restype = C.c_double
+    L.gpv_oracle_ic0.argtypes = [C.c_long, dp, dp, dp]
+    L.gpv_oracle_ic0.restype = C.c_long
+    L.gpv_oracle_createUcpp.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, C.c_int, dp]
+    L.gpv_oracle_createUcpp.restype = C.c_long
     lp = _find_lapack()
     if lp is not None:
         L.gpv_oracle_bind_lapack(lp.encode())
@@ -165,3 +169,32 @@ def block_cond_proxy(k, locs, revNNarray, revCondOnLatent, nuggets, covType, cov
     return float(lib().gpv_oracle_block_cond_proxy(
         int(k), N, d, p, _colmajor(locs, np.float64), _colmajor(revNNarray, np.int32),
         _colmajor(revCondOnLatent, np.float64), _f64(nuggets), covType.encode(), _f64(covparms)))
+
+
+def ic0(ptrs, inds, vals):
+    """src/ic0.cpp:43-63 ; ptrs (N+1), inds, vals as R numeric vectors (0-based indices held in
+    doubles).  Returns the incomplete-Cholesky values (the input is not modified)."""
+    ptrs, inds = _f64(ptrs), _f64(inds)
+    out = _f64(vals).copy()
+    nerr = lib().gpv_oracle_ic0(ptrs.size - 1, ptrs, inds, out)
+    if nerr:
+        raise ValueError(f"ic0: {nerr} entries right of the diagonal (the reference prints ERROR)")
+    return out
+
+
+def createUcppM(ptrs, inds, cov_vals):
+    """src/ic0.cpp:68-71."""
+    return ic0(ptrs, inds, cov_vals)
+
+
+def createUcpp(ptrs, inds, locsord, covparams, fill_only=False):
+    """src/ic0.cpp:77-92 ; locsord (N, d); covparams = (sig2, range, smooth)."""
+    ptrs, inds = _f64(ptrs), _f64(inds)
+    locs = np.asarray(locsord, dtype=np.float64)
+    N, d = locs.shape
+    out = np.zeros(inds.size, dtype=np.float64)
+    nerr = lib().gpv_oracle_createUcpp(N, d, ptrs, inds, _colmajor(locs, np.float64), _f64(covparams),
+                                       int(bool(fill_only)), out)
+    if nerr:
+        raise ValueError(f"createUcpp: {nerr} entries right of the diagonal")
+    return out

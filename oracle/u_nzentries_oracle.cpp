@@ -391,4 +391,49 @@ double gpv_oracle_block_cond_proxy(long k, long Nlocs, int d, int p, const doubl
   return (mx / mn) * (mx / mn);
 }
 
+// ---- src/ic0.cpp : incomplete Cholesky on a fixed pattern (the MRA branch of createU, createU.R:89-140)
+// Restated line by line; indices are doubles because the reference takes Rcpp NumericVectors.
+// dot_prod (:15-29): merge of two index ranges [l1, u1] and [l2, u2] (inclusive), both ascending.
+static double ic0_dot_prod(long l1, long u1, long l2, long u2, const double* row_inds, const double* cells) {
+  double result = 0.0;
+  while (l1 <= u1 && l2 <= u2) {
+    if (row_inds[l1] == row_inds[l2]) { result += cells[l1] * cells[l2]; l1++; l2++; }
+    else if (row_inds[l1] < row_inds[l2]) l1++;
+    else l2++;
+  }
+  return result;
+}
+// ic0 (:43-63): ptrs has N + 1 entries, vals is overwritten; returns the number of entries right of the
+// diagonal (the reference prints "ERROR" for each and leaves the value alone, :57-58).
+long gpv_oracle_ic0(long N, const double* ptrs, const double* inds, double* vals) {
+  long nerr = 0;
+  for (long i = 0; i < N; ++i) {
+    for (long j = (long)ptrs[i]; j < (long)ptrs[i + 1]; ++j) {
+      const long u1 = (long)ptrs[i];
+      const long u2 = (long)ptrs[(long)inds[j]];
+      const double dp = ic0_dot_prod(u1, (long)ptrs[i + 1] - 2, u2, (long)ptrs[(long)inds[j] + 1] - 2, inds, vals);
+      if (inds[j] < i) vals[j] = (vals[j] - dp) / vals[(long)ptrs[(long)inds[j] + 1] - 1];
+      else if (inds[j] == i) vals[j] = std::sqrt(vals[j] - dp);
+      else nerr++;
+    }
+  }
+  return nerr;
+}
+// createUcpp (:77-92): Matern covariance of every (row, stored column) pair, then ic0.  locsord is
+// N x d column-major.  fill_only != 0 stops before ic0 (to check the covariance fill by itself).
+long gpv_oracle_createUcpp(long N, int d, const double* ptrs, const double* inds, const double* locsord,
+                           const double* covparams, int fill_only, double* vals) {
+  std::vector<double> a(d), b(d);
+  for (long i = 0; i < N; ++i) {
+    for (long j = (long)ptrs[i]; j < (long)ptrs[i + 1]; ++j) {
+      const long c = (long)inds[j];
+      for (int k = 0; k < d; ++k) { a[k] = locsord[i + (size_t)k * N]; b[k] = locsord[c + (size_t)k * N]; }
+      const double D = dist_rows<double>(a.data(), b.data(), d);   // :84
+      MaternFun(&D, 1, covparams, vals + j);                       // :85
+    }
+  }
+  return fill_only ? 0 : gpv_oracle_ic0(N, ptrs, inds, vals);      // :89
+}
+
+
 }  // extern "C"

@@ -216,6 +216,40 @@ SEXP gpvb200_MaternFun(SEXP distmat, SEXP covparms) {
   return out;
 }
 
+/* ---- ic0 / createUcppM / createUcpp: same names, arguments and aliasing as src/ic0.cpp:43-92 -------
+ * The reference's NumericVector arguments wrap the R vectors without a copy, so ic0 overwrites `vals` in
+ * place and returns it (createUcppM depends on that, :69-70); the shim keeps that behaviour for a
+ * double vector and works on a coerced copy otherwise, as Rcpp would. */
+static SEXP as_real(SEXP x, int* nprot) {
+  if (TYPEOF(x) == REALSXP) return x;
+  SEXP y = PROTECT(Rf_coerceVector(x, REALSXP));
+  (*nprot)++;
+  return y;
+}
+SEXP gpvb200_ic0(SEXP ptrs, SEXP inds, SEXP vals) {
+  int np = 0;
+  SEXP p = as_real(ptrs, &np), i = as_real(inds, &np), v = as_real(vals, &np);
+  if (XLENGTH(v) != XLENGTH(i)) { UNPROTECT(np); Rf_error("ic0: vals and inds differ in length"); }
+  gpv_status st = gpv_ic0((int64_t)XLENGTH(p) - 1, REAL(p), REAL(i), (int64_t)XLENGTH(i), REAL(v));
+  UNPROTECT(np);
+  check(st);
+  return v;
+}
+SEXP gpvb200_createUcppM(SEXP ptrs, SEXP inds, SEXP cov_vals) { return gpvb200_ic0(ptrs, inds, cov_vals); }
+SEXP gpvb200_createUcpp(SEXP ptrs, SEXP inds, SEXP locsord, SEXP covparams) {
+  int np = 0;
+  SEXP p = as_real(ptrs, &np), i = as_real(inds, &np), l = as_real(locsord, &np), c = as_real(covparams, &np);
+  const int64_t N = (int64_t)XLENGTH(p) - 1;
+  if (!Rf_isMatrix(l) || Rf_nrows(l) != N || XLENGTH(c) < 3) { UNPROTECT(np); Rf_error("createUcpp: locsord must be an N x d matrix and covparams = c(sig2, range, smooth)"); }
+  SEXP vals = PROTECT(Rf_allocVector(REALSXP, XLENGTH(i)));
+  np++;
+  gpv_status st = gpv_createUcpp(N, Rf_ncols(l), REAL(p), REAL(i), (int64_t)XLENGTH(i), REAL(l), REAL(c), REAL(vals),
+                                 device_from_option());
+  UNPROTECT(np);
+  check(st);
+  return vals;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_U_NZentries", (DL_FUNC)&gpvb200_U_NZentries, 9},   /* same name and arity as
                                                                        src/RcppExports.cpp:159 */
@@ -229,6 +263,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_b200_set_scalar_nugget", (DL_FUNC)&gpvb200_set_scalar_nugget, 2},
     {"_GPvecchia_b200_loglik_numerator", (DL_FUNC)&gpvb200_loglik_numerator, 7},
     {"_GPvecchia_b200_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},
+    {"_GPvecchia_ic0", (DL_FUNC)&gpvb200_ic0, 3},                   /* src/RcppExports.cpp: same names and arities */
+    {"_GPvecchia_createUcppM", (DL_FUNC)&gpvb200_createUcppM, 3},
+    {"_GPvecchia_createUcpp", (DL_FUNC)&gpvb200_createUcpp, 4},
     {NULL, NULL, 0}};
 
 void R_init_GPvecchiaB200(DllInfo* dll) {
