@@ -55,3 +55,9 @@ loglik_numerator_b200 <- function(z, vecchia.approx, covparms, nuggets.all.ord, 
              z[vecchia.approx$ord.z], skip)
   list(quadform.num = r[1], logdet.num = r[2], nfail = r[3])
 }
+
+## the MRA branch (R/createU.R:89-106) needs no R change: the shim registers `_GPvecchia_ic0`,
+## `_GPvecchia_createUcppM` and `_GPvecchia_createUcpp` under the reference's own names and arities
+## (R/RcppExports.R:53-63), so `createUcpp(ptrs, inds, locsord, covparms)` evaluates the covariances of
+## the stored entries on the GPU and returns the incomplete-Cholesky values exactly where
+## `Laux = sparseMatrix(j = inds, p = ptrs, x = vals, index1 = FALSE)` (createU.R:109) expects them.
