@@ -28,6 +28,12 @@ namespace gpv {
 #define GPV_BAND_MINB3 3
 #endif
 constexpr int kBandPairUnroll = GPV_BAND_PAIR_UNROLL;   // pair-stage iterations per loop trip
+// GPV_BAND_EARLY_RCP = 1 (experiment, not measured yet: DESIGN.md 9): the owner of row k+1 inverts its pivot
+// as soon as step k has updated it and publishes 1/d_{k+1} in the diagonal slot, so a step starts with
+// loads and a multiply instead of load -> MUFU.RCP64H -> 3 DFMA.  Same values as the default path.
+#ifndef GPV_BAND_EARLY_RCP
+#define GPV_BAND_EARLY_RCP 0
+#endif
 
 template <int G, int P, int D>
 struct BandLayout {
@@ -387,6 +393,15 @@ u_band_kernel(const UParams q) {
     bool fail = false;
     double dlast = 1.0;
     double inv_prev = 0.0;
+    auto bad_pivot = [](double v) { return (unsigned)(__double2hiint(v) - 0x00100000) >= 0x7fe00000u; };
+#if GPV_BAND_EARLY_RCP
+    {
+      // column 0 is the staged matrix: its pivot sits in a0[0] of the lane that holds row 0
+      const double inv0 = rcp_pos(a0[0]);
+      if (gl == band_owner<G>(0)) { fail = bad_pivot(a0[0]); buf[tri_col(0, P)] = inv0; }
+      __syncwarp();
+    }
+#endif
 #define GPV_B_UPD(J, W)                                                                   \
     do {                                                                                  \
       if ((J) < S0) a0[(J) < S0 ? (J) : 0] = fma(-m0, (W), a0[(J) < S0 ? (J) : 0]);         \
@@ -414,18 +429,42 @@ u_band_kernel(const UParams q) {
           wa = buf[ck + k + 1]; j = k + 2;
         }
       }
+#if GPV_BAND_EARLY_RCP
+      // the diagonal slot already holds 1 / d_k (d_k itself for the last column); the pivot was tested by
+      // its owner when it became final
+      if (k == P - 1) { dlast = akk; break; }
+      const double inv = akk;
+      (void)inv_prev;
+#else
       // positive, normal, finite -- dpotrf's `ajj <= 0 || isnan(ajj)` test on the integer pipe
-      fail = fail || ((unsigned)(__double2hiint(akk) - 0x00100000) >= 0x7fe00000u);
+      fail = fail || bad_pivot(akk);
       if (k >= 1 && gl == band_owner<G>(k >= 1 ? k - 1 : 0)) buf[tri_col(k >= 1 ? k - 1 : 0, P)] = inv_prev;
       if (k == P - 1) { dlast = akk; break; }
       const double inv = rcp_pos(akk);      // an Inf nugget arrives here as 1e300 (clamp_nugget)
       inv_prev = inv;
+#endif
       const double m0 = (k < S0) ? a0[k < S0 ? k : 0] * inv : 0.0;
       const double m1 = (k < S1) ? a1[k < S1 ? k : 0] * inv : 0.0;
       const double m2 = (k < S2) ? a2[k < S2 ? k : 0] * inv : 0.0;
       const double m3 = (NB > 3 && k < S3) ? a3[k < S3 ? k : 0] * inv : 0.0;
       // column k+1: update, publish
       GPV_B_UPD(k + 1, wa);
+#if GPV_BAND_EARLY_RCP
+      {
+        // as below, except that row k+1 itself publishes 1 / d_{k+1} (d_{k+1} for the last column) in
+        // place of the pivot; its owner tests the pivot (dpotrf's `ajj <= 0 || isnan(ajj)`)
+        const int kb = band_of<G>(k + 1 < P ? k + 1 : P - 1);
+        const double piv = (kb == 0) ? a0[k + 1 < S0 ? k + 1 : 0] : (kb == 1) ? a1[k + 1 < S1 ? k + 1 : 0]
+                         : (kb == 2) ? a2[k + 1 < S2 ? k + 1 : 0] : a3[k + 1 < S3 ? k + 1 : 0];
+        const double dval = (k + 1 == P - 1) ? piv : rcp_pos(piv);
+        if (gl == band_owner<G>(k + 1 < P ? k + 1 : P - 1)) fail = fail || bad_pivot(piv);
+        const int cn = tri_col(k + 1, P) - (k + 1);
+        if (k + 1 < S0 && rc[0] >= k + 1) buf[cn + rc[0]] = (kb == 0 && rc[0] == k + 1) ? dval : a0[k + 1 < S0 ? k + 1 : 0];
+        if (k + 1 < S1 && rc[1] >= k + 1) buf[cn + rc[1]] = (kb == 1 && rc[1] == k + 1) ? dval : a1[k + 1 < S1 ? k + 1 : 0];
+        if (k + 1 < S2 && (NB > 3 || vb[2]) && rc[2] >= k + 1) buf[cn + rc[2]] = (kb == 2 && rc[2] == k + 1) ? dval : a2[k + 1 < S2 ? k + 1 : 0];
+        if (NB > 3 && k + 1 < S3 && v3 && rc3 >= k + 1) buf[cn + rc3] = (kb == 3 && rc3 == k + 1) ? dval : a3[k + 1 < S3 ? k + 1 : 0];
+      }
+#else
       {
         const int cn = tri_col(k + 1, P) - (k + 1);
         if (k + 1 < S0 && rc[0] >= k + 1) buf[cn + rc[0]] = a0[k + 1 < S0 ? k + 1 : 0];
@@ -433,6 +472,7 @@ u_band_kernel(const UParams q) {
         if (k + 1 < S2 && (NB > 3 || vb[2]) && rc[2] >= k + 1) buf[cn + rc[2]] = a2[k + 1 < S2 ? k + 1 : 0];
         if (NB > 3 && k + 1 < S3 && v3 && rc3 >= k + 1) buf[cn + rc3] = a3[k + 1 < S3 ? k + 1 : 0];
       }
+#endif
       // the rest of the trailing update: a[r][j] -= m_r a[j][k]
       if (j == k + 3) GPV_B_UPD(k + 2, wb);
 #pragma unroll
@@ -448,6 +488,9 @@ u_band_kernel(const UParams q) {
       __syncwarp();
     }
 #undef GPV_B_UPD
+#if GPV_BAND_EARLY_RCP
+    fail = ((__ballot_sync(FULL, fail) >> base) & GMASK) != 0u;   // pivots were tested by their owners only
+#endif
     __syncwarp();
 
     // ---- 6. x = L^{-T} e_P / sqrt(d_P)  (solve(R, onevec), U_NZentries.cpp:62): unit-triangular column
