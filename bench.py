@@ -507,6 +507,8 @@ def main():
             pj = json.load(open(prof))
             roofline["traffic"] = pj.get("dram_bytes_per_launch")
             roofline["fp64_pipe_active_pct_ncu"] = pj.get("fp64_pipe_pct_of_peak_active")
+            if pj.get("note"):
+                roofline["ncu_note"] = pj["note"]
         except Exception:
             pass
 
