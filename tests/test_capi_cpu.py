@@ -114,3 +114,22 @@ def test_general_nu_table_against_mpmath_golden():
         # forming w = (s*range)^2 and back perturbs s by ~2 ulp: allow s*4e-16 on top of 1e-14
         worst = max(worst, abs(got - val) / abs(val) / max(1.0, s))
     assert worst < 2e-14, worst
+
+
+def test_r_shim_type_checks_against_the_c_abi():
+    """r_shim/src/gpv_shim.c cannot be built here (no R), but its calls into include/gpvecchia_b200.h can
+    be type-checked: `gcc -fsyntax-only` against declarations of the R API subset it uses
+    (tests/r_api_mock, written from the R-extensions manual).  Catches a shim that drifts from the C ABI."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "r_api_mock"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r_shim", "src", "gpv_shim.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "r_shim", "src", "gpv_shim.c")).read()
+    # the reference's own .Call names stay registered with the reference's arities (src/RcppExports.cpp)
+    for name, arity in (("_GPvecchia_U_NZentries", 9), ("_GPvecchia_U_NZentries_mat", 9), ("_GPvecchia_ic0", 3),
+                        ("_GPvecchia_createUcppM", 3), ("_GPvecchia_createUcpp", 4)):
+        assert re.search(r'\{"%s",\s*\(DL_FUNC\)&\w+,\s*%d\}' % (name, arity), src), name
