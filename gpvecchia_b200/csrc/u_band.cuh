@@ -178,7 +178,11 @@ u_band_kernel(const UParams q) {
   constexpr unsigned GMASK = (1u << G) - 1u;
   constexpr int kSelfLane = band_owner<G>(P - 1);    // lane that holds row P-1 (last band)
 
+#ifdef GPV_SIMT_EMU
+  double* smem = emu_dynamic_smem();                          // provided by the host harness (tests/simt_emu)
+#else
   extern __shared__ __align__(16) double smem[];
+#endif
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / G;

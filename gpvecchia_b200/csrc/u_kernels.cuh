@@ -119,9 +119,13 @@ __constant__ double kExp2Tab[64] = GPV_EXP2_TAB_INIT;   // 2^(j/64), copied to s
 #endif
 
 __device__ __forceinline__ double rsqrt_seed(double a) {
+#ifdef GPV_SIMT_EMU
+  return emu_rsqrt_seed(a);                                  // host model of the seed (tests/simt_emu)
+#else
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, ~20 good bits
   return y;
+#endif
 }
 // 1/sqrt(a) for finite normal a > 0 to ~1 ulp: cubic step (+ a Newton step).
 // a <= 0 / NaN / Inf: garbage, callers test `a > 0` themselves (nuggets are clamped at 1e300).
@@ -145,7 +149,11 @@ __device__ __forceinline__ double clamp_nugget(double v) { return (v > 1.0e300) 
 // error 2^-19.9, tools/microbench/lat.cu); a <= 0 / NaN / Inf: garbage, callers test the pivot.
 __device__ __forceinline__ double rcp_pos(double a) {
   double y0;
+#ifdef GPV_SIMT_EMU
+  y0 = emu_rcp_seed(a);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+#endif
   const double e = fma(-a, y0, 1.0);
   return fma(fma(e, e, e), y0, y0);                          // y0 (1 + e + e^2): error ~ e^3 = 2^-60
 }
@@ -531,7 +539,11 @@ u_sets_kernel(const UParams q) {
   constexpr int SETS = LY::kSetsPerWarp;
   constexpr unsigned FULL = 0xffffffffu;
 
+#ifdef GPV_SIMT_EMU
+  double* smem = emu_dynamic_smem();                          // provided by the host harness (tests/simt_emu)
+#else
   extern __shared__ __align__(16) double smem[];
+#endif
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / G;
