@@ -240,3 +240,35 @@ def test_shared_memory_protocol_is_race_free_under_thread_sanitizer(tmp_path, de
         subprocess.check_call(base + ["-DGPV_EMU_DROP_SYNCWARP"] + srcs + ["-o", bad])
         rb = subprocess.run([bad], capture_output=True, text=True, timeout=600)
         assert "ThreadSanitizer: data race" in rb.stderr + rb.stdout
+
+
+def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
+    """Seeded sweep through the emulated band kernel: set sizes p = 17..31 on the P = 31 instantiation, holes
+    anywhere, mixed latent / response conditioning, and nuggets that include Inf on response-conditioned
+    neighbours (Vecchia-Laplace's missing data, vecchia_laplace_NR.R:108: that neighbour decouples)."""
+    L = _build(emu_dir)
+    rng = np.random.default_rng(20240601)
+    for trial in range(6):
+        m = int(rng.integers(16, 31))
+        n = 64
+        locs, revNN, rcf = _problem(n, m, 2, seed=100 + trial, layout="z", p_drop=float(rng.choice([0.0, 0.15])))
+        p = m + 1
+        # mixed conditioning inside the valid (last n0) columns; self stays latent
+        for k in range(n):
+            k0 = int((revNN[k] != 0).sum())
+            flip = rng.random(k0 - 1) < 0.3
+            rcf[k, p - k0:p - 1][flip] = 1.0
+        nug = rng.uniform(0.05, 0.2, n)
+        if trial % 2 == 1:
+            nug[rng.integers(0, n, 3)] = np.inf
+        cp = [float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.2, 0.6)), float(rng.choice([0.5, 1.5, 2.5]))]
+        ref = _oracle(locs, revNN, rcf, nug, "matern", cp, mode=1)
+        got, _, nfail, _, n0 = _run(L, 8, 31, locs, revNN, rcf, nug, "matern", cp)
+        got = got.reshape(n, p)
+        Lr = ref["Lentries"]
+        failed = np.array([np.all(Lr[k, :n0[k]] == 0) for k in range(n)])
+        assert nfail == ref["nfail"] == int(failed.sum()), (trial, nfail, ref["nfail"])
+        ok = ~failed
+        scale = np.abs(Lr[ok]).max(axis=1, keepdims=True)
+        assert (np.abs(got[ok] - Lr[ok]) / scale).max() < 1e-9, trial
+        assert np.all(got[failed] == 0)
