@@ -366,208 +366,7 @@ u_band_kernel(const UParams q) {
       if (vb[b]) buf[tri_col(rc[b], P)] = dg[b];
     __syncwarp();
 
-    // ---- 4. my rows of the lower triangle into registers (entries beyond the diagonal: stale, never
-    // used) ----------------------------------------------------------------------------------------------
-    const int rc3 = (NB > 3) ? rc[NB - 1] : 0;
-    const bool v3 = (NB > 3) ? vb[NB - 1] : false;
-    double a0[S0], a1[S1], a2[S2], a3[S3];
-#pragma unroll
-    for (int j = 0; j < S0; ++j) a0[j] = buf[tri_col(j, P) + rc[0] - j];
-#pragma unroll
-    for (int j = 0; j < S1; ++j) a1[j] = buf[tri_col(j, P) + rc[1] - j];
-#pragma unroll
-    for (int j = 0; j < S2; ++j) a2[j] = buf[tri_col(j, P) + rc[2] - j];
-    if constexpr (NB > 3) {
-#pragma unroll
-      for (int j = 0; j < S3; ++j) a3[j] = buf[tri_col(j, P) + rc3 - j];
-    } else {
-      a3[0] = 0.0;
-    }
-    __syncwarp();
-
-    // ---- 5. right-looking LDL^T (square-root-free Cholesky; chol(covmat,"upper"), U_NZentries.cpp:61)
-    // Sigma = L D L^T.  Columns are published to shared memory UNSCALED (a[r][k] = L[r][k] d_k), as soon
-    // as they are final: column k+1 is the first thing step k updates, and it is stored before the rest
-    // of the trailing update is issued.  Every lane then reads the pivot a[k][k] and the column back as
-    // group-broadcast loads and scales its own multipliers m = a[r][k] / d_k.  No shuffle and no
-    // reciprocal sit between a column becoming final and its publication, which is what bounds a step
-    // when only two warps share a scheduler.  Column 0 is the staged matrix itself.  1 / d_k replaces
-    // the pivot in its diagonal slot one step later (nobody reads that slot in between), for the sweep.
-    // A pivot that is not > 0 (or NaN) is dpotrf's failure.
-    bool fail = false;
-    double dlast = 1.0;
-    double inv_prev = 0.0;
-    auto bad_pivot = [](double v) { return (unsigned)(__double2hiint(v) - 0x00100000) >= 0x7fe00000u; };
-#if GPV_BAND_EARLY_RCP
-    {
-      // column 0 is the staged matrix: its pivot sits in a0[0] of the lane that holds row 0
-      const double inv0 = rcp_pos(a0[0]);
-      if (gl == band_owner<G>(0)) { fail = bad_pivot(a0[0]); buf[tri_col(0, P)] = inv0; }
-      __syncwarp();
-    }
-#endif
-#define GPV_B_UPD(J, W)                                                                   \
-    do {                                                                                  \
-      if ((J) < S0) a0[(J) < S0 ? (J) : 0] = fma(-m0, (W), a0[(J) < S0 ? (J) : 0]);         \
-      if ((J) < S1) a1[(J) < S1 ? (J) : 0] = fma(-m1, (W), a1[(J) < S1 ? (J) : 0]);         \
-      if ((J) < S2) a2[(J) < S2 ? (J) : 0] = fma(-m2, (W), a2[(J) < S2 ? (J) : 0]);         \
-      if (NB > 3 && (J) < S3) a3[(J) < S3 ? (J) : 0] = fma(-m3, (W), a3[(J) < S3 ? (J) : 0]); \
-    } while (0)
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-      const int ck = tri_col(k, P) - k;     // a[r][k] at buf[ck + r], r >= k
-      double akk, wa = 0.0, wb = 0.0;       // pivot, a[k+1][k], a[k+2][k]
-      int j;                                // first column of the paired loop
-      if (k == P - 1) {
-        akk = buf[ck + k];
-        j = P;
-      } else if (((ck + k) & 1) == 0) {
-        const double2 l2 = *reinterpret_cast<const double2*>(&buf[ck + k]);
-        akk = l2.x; wa = l2.y; j = k + 2;
-      } else {
-        akk = buf[ck + k];
-        if (k + 2 < P) {
-          const double2 l2 = *reinterpret_cast<const double2*>(&buf[ck + k + 1]);
-          wa = l2.x; wb = l2.y; j = k + 3;
-        } else {
-          wa = buf[ck + k + 1]; j = k + 2;
-        }
-      }
-#if GPV_BAND_EARLY_RCP
-      // the diagonal slot already holds 1 / d_k (d_k itself for the last column); the pivot was tested by
-      // its owner when it became final
-      if (k == P - 1) { dlast = akk; break; }
-      const double inv = akk;
-      (void)inv_prev;
-#else
-      // positive, normal, finite -- dpotrf's `ajj <= 0 || isnan(ajj)` test on the integer pipe
-      fail = fail || bad_pivot(akk);
-      if (k >= 1 && gl == band_owner<G>(k >= 1 ? k - 1 : 0)) buf[tri_col(k >= 1 ? k - 1 : 0, P)] = inv_prev;
-      if (k == P - 1) { dlast = akk; break; }
-      const double inv = rcp_pos(akk);      // an Inf nugget arrives here as 1e300 (clamp_nugget)
-      inv_prev = inv;
-#endif
-      const double m0 = (k < S0) ? a0[k < S0 ? k : 0] * inv : 0.0;
-      const double m1 = (k < S1) ? a1[k < S1 ? k : 0] * inv : 0.0;
-      const double m2 = (k < S2) ? a2[k < S2 ? k : 0] * inv : 0.0;
-      const double m3 = (NB > 3 && k < S3) ? a3[k < S3 ? k : 0] * inv : 0.0;
-      // column k+1: update, publish
-      GPV_B_UPD(k + 1, wa);
-#if GPV_BAND_EARLY_RCP
-      {
-        // as below, except that row k+1 itself publishes 1 / d_{k+1} (d_{k+1} for the last column) in
-        // place of the pivot; its owner tests the pivot (dpotrf's `ajj <= 0 || isnan(ajj)`)
-        const int kb = band_of<G>(k + 1 < P ? k + 1 : P - 1);
-        const double piv = (kb == 0) ? a0[k + 1 < S0 ? k + 1 : 0] : (kb == 1) ? a1[k + 1 < S1 ? k + 1 : 0]
-                         : (kb == 2) ? a2[k + 1 < S2 ? k + 1 : 0] : a3[k + 1 < S3 ? k + 1 : 0];
-        const double dval = (k + 1 == P - 1) ? piv : rcp_pos(piv);
-        if (gl == band_owner<G>(k + 1 < P ? k + 1 : P - 1)) fail = fail || bad_pivot(piv);
-        const int cn = tri_col(k + 1, P) - (k + 1);
-        if (k + 1 < S0 && rc[0] >= k + 1) buf[cn + rc[0]] = (kb == 0 && rc[0] == k + 1) ? dval : a0[k + 1 < S0 ? k + 1 : 0];
-        if (k + 1 < S1 && rc[1] >= k + 1) buf[cn + rc[1]] = (kb == 1 && rc[1] == k + 1) ? dval : a1[k + 1 < S1 ? k + 1 : 0];
-        if (k + 1 < S2 && (NB > 3 || vb[2]) && rc[2] >= k + 1) buf[cn + rc[2]] = (kb == 2 && rc[2] == k + 1) ? dval : a2[k + 1 < S2 ? k + 1 : 0];
-        if (NB > 3 && k + 1 < S3 && v3 && rc3 >= k + 1) buf[cn + rc3] = (kb == 3 && rc3 == k + 1) ? dval : a3[k + 1 < S3 ? k + 1 : 0];
-      }
-#else
-      {
-        const int cn = tri_col(k + 1, P) - (k + 1);
-        if (k + 1 < S0 && rc[0] >= k + 1) buf[cn + rc[0]] = a0[k + 1 < S0 ? k + 1 : 0];
-        if (k + 1 < S1 && rc[1] >= k + 1) buf[cn + rc[1]] = a1[k + 1 < S1 ? k + 1 : 0];
-        if (k + 1 < S2 && (NB > 3 || vb[2]) && rc[2] >= k + 1) buf[cn + rc[2]] = a2[k + 1 < S2 ? k + 1 : 0];
-        if (NB > 3 && k + 1 < S3 && v3 && rc3 >= k + 1) buf[cn + rc3] = a3[k + 1 < S3 ? k + 1 : 0];
-      }
-#endif
-      // the rest of the trailing update: a[r][j] -= m_r a[j][k]
-      if (j == k + 3) GPV_B_UPD(k + 2, wb);
-#pragma unroll
-      for (; j + 1 < P; j += 2) {           // 16-byte aligned broadcast loads for (j, j+1)
-        const double2 l2 = *reinterpret_cast<const double2*>(&buf[ck + j]);
-        GPV_B_UPD(j, l2.x);
-        GPV_B_UPD(j + 1, l2.y);
-      }
-      if (j < P) {
-        const double l1 = buf[ck + j];
-        GPV_B_UPD(j, l1);
-      }
-      __syncwarp();
-    }
-#undef GPV_B_UPD
-#if GPV_BAND_EARLY_RCP
-    fail = ((__ballot_sync(FULL, fail) >> base) & GMASK) != 0u;   // pivots were tested by their owners only
-#endif
-    __syncwarp();
-
-    // ---- 6. x = L^{-T} e_P / sqrt(d_P)  (solve(R, onevec), U_NZentries.cpp:62): unit-triangular column
-    // sweep on t = -y, t_r = -sum_{j > r} L[j][r] t_j with L[j][r] = a[j][r] / d_r rebuilt from the
-    // unscaled column and the reciprocal in its diagonal slot; the unit right-hand side enters as
-    // t_{P-1} = -1 on the lane that holds row P-1.
-    double s[NB];
-    int cb[NB];
-    double invd[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      s[b] = (b == NB - 1 && gl == kSelfLane) ? -1.0 : 0.0;
-      cb[b] = tri_col(rc[b], P) - rc[b];
-      invd[b] = buf[tri_col(rc[b], P)];
-    }
-#pragma unroll
-    for (int j = P - 1; j >= 1; --j) {
-      const double tj = __shfl_sync(FULL, s[band_of<G>(j)], base + band_owner<G>(j));
-      // L[j][r] = a[j][r] / d_r, a[j][r] at buf[tri_col(r) - r + j]; band b holds rows bG..bG+G-1
-#pragma unroll
-      for (int b = 0; b < NB; ++b)
-        if (j > G * b && rc[b] < j) s[b] = fma(-(buf[cb[b] + j] * invd[b]), tj, s[b]);
-    }
-    const double rs = rsqrt_pos(dlast);
-    double xo[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) xo[b] = fail ? 0.0 : -s[b] * rs;   // failed row stays zero (:64-66)
-
-    // ---- 7. outputs ------------------------------------------------------------------------------------
-    if (fail && row_ok && gl == 0 && n0 > 0) {
-      atomicAdd(q.nfail, 1ull);
-      atomicMin(q.first_fail, (long long)(q.row0 + row));
-    }
-    if (q.out != nullptr && row_ok) {
-      if (q.row_off != nullptr) {
-        double* o = q.out + q.row_off[row];
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          if (id[b] >= 0) o[rc[b] - npad] = xo[b];
-      } else {
-        double* o = q.out + (int64_t)row * p;
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          if (id[b] >= 0) o[rc[b] - npad] = xo[b];
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (gl + G * c >= n0 && gl + G * c < p) o[gl + G * c] = 0.0;   // zero fill beyond n0 (:33)
-      }
-    }
-    if (q.partials != nullptr) {
-      // quadform.num: (sum_{j: revCond = 0} x_j z_j)^2 ; logdet.num: log x_self (vecchia_likelihood.R:74-76)
-      const double* zst = st + LY::kOffZ;
-      double t = 0.0;
-#pragma unroll
-      for (int b = 0; b < NB; ++b)
-        if (id[b] >= 0 && !cd[b]) t = fma(xo[b], zst[rc[b]], t);
-#pragma unroll
-      for (int o = G / 2; o >= 1; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-      const double xself = __shfl_sync(FULL, xo[NB - 1], base + kSelfLane);
-      if (gl == 0 && row_ok && n0 > 0 && (q.row0 + row) >= q.skip_rows) {
-        acc_quad += t * t;
-        acc_logd += log(xself);
-        if (q.full_z) {
-          // pure `z` conditioning: U_y U_y^T is diagonal, W_kk = x_kk^2 + 1/tau_k, and
-          // z2_k = x_kk q_k - z_k / tau_k (vecchia_likelihood.R:85-91 per row)
-          const double tau = nugs[P - 1], zk = zst[P - 1];
-          const double w = fma(xself, xself, 1.0 / tau);
-          const double z2 = fma(xself, t, -zk / tau);
-          acc_qden += z2 * z2 / w;
-          acc_lden += log(w);
-        }
-      }
-    }
+#include "u_band_factor.inc"
     __pipeline_wait_prior(0);                              // set i+1 staged, ids of set i+2 landed
     __syncwarp();
     n0 = n0_next;
