@@ -80,17 +80,20 @@ static void register_all() {
   register_kernels_B8_31(g_entries, &g_nentries);
   register_kernels_B8_32(g_entries, &g_nentries);
   register_kernels_B16_41(g_entries, &g_nentries);
+  register_kernels_WS(g_entries, &g_nentries);
 }
 const KernelEntry* select_kernel(int p, int d, bool general) {
   std::call_once(g_reg_once, register_all);
   const int want_d = (d == 2 || d == 3) ? d : 0;
   const char* fam = std::getenv("GPV_KERNEL_FAMILY");
   const bool no_band = fam && std::strcmp(fam, "fold") == 0;
+  const bool want_ws = fam && std::strcmp(fam, "ws") == 0;     // development knob: the warp-specialised experiment
   const KernelEntry* best = nullptr;
   for (int i = 0; i < g_nentries; ++i) {
     const KernelEntry& e = g_entries[i];
     if (e.D != want_d || e.P < p || e.general != general) continue;
     if (e.family == 1 && no_band) continue;
+    if (e.family == 2 && !want_ws) continue;
     if (!best || e.P < best->P || (e.P == best->P && e.family > best->family)) best = &e;
   }
   return best;
@@ -601,7 +604,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaFuncSetAttribute((const void*)entry->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              entry->smem_bytes));
   H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, (const void*)entry->kernel,
-                                                      kThreadsPerBlock, entry->smem_bytes));
+                                                      entry->threads, entry->smem_bytes));
   if (h->blocks_per_sm < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry->name); }
   h->max_blocks = h->num_sms * h->blocks_per_sm;
   {
@@ -940,7 +943,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   const bool general = (q.cov == COV_GENERAL);
   const KernelEntry* e = general ? h->entry_gen : h->entry;
   const int cap = general ? h->max_blocks_gen : h->num_sms * h->blocks_per_sm;
-  const int sets_per_block = kWarpsPerBlock * (32 / e->G);
+  const int sets_per_block = e->sets_per_block ? e->sets_per_block : kWarpsPerBlock * (32 / e->G);
   int64_t want = (q.nsets + sets_per_block - 1) / sets_per_block;
   int cap_eff = cap;
   if (const char* env = std::getenv("GPV_BLOCKS_PER_SM")) {      // development knob: occupancy experiments
@@ -955,7 +958,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   }
   const int slot = (int)(h->n_launch % gpv_handle::kRing);
   CUDA_TRY(cudaEventRecord(h->ev_start[slot], st));
-  e->kernel<<<blocks, kThreadsPerBlock, e->smem_bytes, st>>>(q);
+  e->kernel<<<blocks, e->threads, e->smem_bytes, st>>>(q);
   g_launches++;
   CUDA_TRY(cudaEventRecord(h->ev_stop[slot], st));
   h->n_launch++;

@@ -10,10 +10,13 @@ namespace gpv {
 struct KernelEntry {
   int G, P, D;                                 // D = 0: runtime d <= GPV_MAX_D
   bool general;                                // general-nu table kernel vs closed forms
-  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: band-folded, three or four rows per lane (u_band.cuh)
+  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: band-folded, three or four rows per lane (u_band.cuh),
+                                               // 2: warp-specialised experiment (u_band_ws.cuh; only with GPV_KERNEL_FAMILY=ws)
   const char* name;
   void (*kernel)(const UParams);
   int smem_bytes;
+  int threads = 128;                           // block size (kThreadsPerBlock for families 0 and 1)
+  int sets_per_block = 0;                      // sets per pass of the persistent loop; 0: kWarpsPerBlock * (32 / G)
 };
 
 // Picks the smallest instantiated P >= p for dimension d (the band-folded family wins a tie unless
@@ -37,5 +40,6 @@ void register_kernels_B8_26(KernelEntry* out, int* n);
 void register_kernels_B8_31(KernelEntry* out, int* n);
 void register_kernels_B8_32(KernelEntry* out, int* n);
 void register_kernels_B16_41(KernelEntry* out, int* n);
+void register_kernels_WS(KernelEntry* out, int* n);
 
 }  // namespace gpv

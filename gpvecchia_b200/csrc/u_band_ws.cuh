@@ -1,0 +1,300 @@
+// u_band_ws.cuh -- EXPERIMENT (candidate 1; not the default path, not yet timed on a B200):
+// a warp-specialised variant of the band-folded set kernel for 24 < P <= 32 (G = 8, four bands).
+//
+// Why: u_band_kernel holds 255 registers and 6.6 KB of shared memory per set, which leaves two warps per
+// scheduler; the fp64 pipe is 47 % busy and what remains is latency inside a warp's dependent phases
+// (profiles/r01_u_band_closed_P31_D2_nu15_phases.txt).  The pair stage needs few registers and has four
+// independent chains per lane; the factorisation needs the registers and sits in step heads.  Here they run in
+// different warps of one 384-thread block:
+//   * warps 0-3 (one warp group, `setmaxnreg.inc` to 240 registers): CONSUMERS.  Each owns two batch slots of
+//     four sets and runs steps 4-7 (u_band_factor.inc, the same text u_band_kernel includes) on a slot once
+//     its four sets are marked full, then marks the slot empty.
+//   * warps 4-11 (two warp groups, `setmaxnreg.dec` to 96): PRODUCERS, warp-per-set.  Producers 2c and 2c+1
+//     fill sets {0,1} and {2,3} of consumer c's next slot: ids -> compaction (one ballot) -> coordinates,
+//     nugget, z of point `lane` -> the lane's 15 or 16 pairs (lane, lane + t mod P), four at a time -> staged
+//     triangle, diagonal, padding -> full.
+// 12 warps per SM instead of 8 inside the same register file (4*32*240 + 8*32*96 = 55 296) and shared memory
+// (32 set buffers of triangle + one input stage = 176 KB).  Slots are handed over through monotone counters in
+// shared memory (release store by one lane after __syncwarp, acquire spin by one lane before __syncwarp).
+// Results are those of u_band_kernel up to the order of nothing: the same pairs, the same arithmetic per pair,
+// the same factorisation text; checked on the host by tests/test_simt_emu.py.
+#pragma once
+#include "u_band.cuh"
+
+namespace gpv {
+
+constexpr int kWsConsumerWarps = 4;
+constexpr int kWsProducerWarps = 8;
+constexpr int kWsThreads = 32 * (kWsConsumerWarps + kWsProducerWarps);
+constexpr int kWsSlots = 2;                      // batches in flight per consumer warp
+constexpr int kWsConsumerRegs = 240, kWsProducerRegs = 96;
+
+template <int P, int D>
+struct WsLayout {
+  using LY = BandLayout<8, P, D>;
+  static constexpr int kSet = ((LY::kBuf + LY::kStage + 15) / 16) * 16 + 16;   // triangle + ONE input stage (+ skew room)
+  static constexpr int kSetBuffers = kWsConsumerWarps * kWsSlots * 4;
+  static constexpr int kBytesPerBlock = kSetBuffers * kSet * 8;
+  static constexpr int kSetsPerBlock = kWsConsumerWarps * 4;                     // per pass of the persistent loop
+  static_assert(P > 24 && P <= 32, "warp-specialised variant: four bands of eight lanes");
+};
+
+// ---- slot hand-over --------------------------------------------------------------------------------------
+__device__ __forceinline__ void ws_signal(int* flag, int value) {   // one lane, after the warp's __syncwarp
+#ifdef GPV_SIMT_EMU
+  __atomic_store_n(flag, value, __ATOMIC_RELEASE);
+#else
+  __threadfence_block();
+  *reinterpret_cast<volatile int*>(flag) = value;
+#endif
+}
+__device__ __forceinline__ void ws_wait(const int* flag, int value) {   // one lane; the warp's __syncwarp follows
+#ifdef GPV_SIMT_EMU
+  while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) < value) sched_yield();
+#else
+  while (*reinterpret_cast<const volatile int*>(flag) < value) __nanosleep(40);
+  __threadfence_block();
+#endif
+}
+template <int REGS> __device__ __forceinline__ void ws_regs_inc() {
+#ifndef GPV_SIMT_EMU
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS));
+#endif
+}
+template <int REGS> __device__ __forceinline__ void ws_regs_dec() {
+#ifndef GPV_SIMT_EMU
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS));
+#endif
+}
+
+// ---- producer: one set by one warp -------------------------------------------------------------------------
+// Pairs of point r = lane: (r, r + t mod P), t = 1..P/2 (for even P the last t only for r < P/2): every unordered
+// pair once, 15 or 16 per lane.  Four values of t per trip give the lane four independent covariance chains.
+template <int KIND, int P, int D>
+static __device__ __noinline__ void ws_pair_stage(CovConsts cc, double* __restrict__ buf, const double* __restrict__ xs,
+                                                  const double (&x)[BandLayout<8, P, D>::DD], int r, int npad,
+                                                  const double* __restrict__ etab, int d) {
+  using LY = BandLayout<8, P, D>;
+  constexpr int T = LY::kT;
+  const double guard = kMathC[7];
+  const int rr = r < P ? r : P - 1;
+#pragma unroll 1
+  for (int t0 = 1; t0 <= T; t0 += 4) {
+    double r2[4], v[4];
+    int off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = (t0 + u <= T) ? t0 + u : T;
+      int j = rr + t; if (j >= P) j -= P;
+      const bool act = (r < P) && (t0 + u <= T) && (2 * t < P || r < P / 2);
+      const int a = rr > j ? rr : j, b = rr > j ? j : rr;
+      // a pair that involves a padding point (leading indices < npad) is a zero of the identity block
+      off[u] = act ? ((b < npad) ? -2 - (tri_col(b, P) + a - b) : tri_col(b, P) + a - b) : -1;
+      r2[u] = pair_r2<D>(xs, LY::PX, x, j, d, guard);
+    }
+    cov_eval_n<KIND, 4>(r2, v, cc, etab);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (off[u] >= 0) buf[off[u]] = v[u];
+      else if (off[u] <= -2) buf[-2 - off[u]] = 0.0;
+    }
+  }
+}
+
+template <int P, int D>
+__device__ __forceinline__ void ws_produce_set(const UParams& q, int64_t sidx, double* __restrict__ buf,
+                                               double* __restrict__ st, const double* __restrict__ etab,
+                                               int lane, int d, int p) {
+  using LY = BandLayout<8, P, D>;
+  constexpr unsigned FULL = 0xffffffffu;
+  int* ids = reinterpret_cast<int*>(st + LY::kOffIds);
+  double* xs = st;
+  double* nug = st + LY::kOffNug;
+  double* zs = st + LY::kOffZ;
+  double* meta = st + LY::kOffMeta;
+  int* metai = reinterpret_cast<int*>(meta + 1);
+  const bool live = sidx < q.nsets;
+  // ids of the row as stored, compaction like inds.elem(find(inds)) (U_NZentries.cpp:41-45): missing entries
+  // become LEADING padding
+  const int raw = (live && lane < p) ? q.nn[sidx * (int64_t)p + lane] : -1;
+  const unsigned bal = __ballot_sync(FULL, raw >= 0);
+  const int n0 = __popc(bal);
+  const int npad = P - n0;
+  if (lane < npad && lane < P) ids[lane] = -1;
+  __syncwarp();
+  if (raw >= 0) ids[npad + __popc(bal & ((1u << lane) - 1u))] = raw;
+  unsigned long long cmask = 0ull;
+  if (lane == 0) {
+    cmask = live ? (unsigned long long)q.cond[sidx] : 0ull;
+    reinterpret_cast<unsigned long long*>(meta)[0] = cmask;
+    metai[0] = live ? (q.rowmap != nullptr ? q.rowmap[sidx] : (int)(q.set_base + sidx)) : -1;
+    metai[1] = n0;
+  }
+  __syncwarp();
+  cmask = reinterpret_cast<const unsigned long long*>(meta)[0];
+  // point r = lane of the compacted set
+  const int r = lane;
+  const int id = (r < P) ? ids[r] : -1;
+  double x[LY::DD];
+#pragma unroll
+  for (int c = 0; c < LY::DD; ++c) x[c] = 0.0;
+  double nv = 0.0, zv = 0.0;
+  if (id >= 0) {
+#pragma unroll
+    for (int c = 0; c < LY::DD; ++c)
+      if (c < d) x[c] = q.locs[(int64_t)id * d + c];
+    nv = q.nuggets[id];
+    if (q.zloc != nullptr) zv = q.zloc[id];
+  }
+  double dg = 1.0;
+  if (r < P) {
+    if (D == 2) {
+      reinterpret_cast<double2*>(xs)[r] = make_double2(x[0], x[1]);
+    } else {
+      for (int c = 0; c < d; ++c) xs[c * LY::PX + r] = x[c];
+    }
+    nug[r] = nv;
+    zs[r] = zv;
+    if (id >= 0) {
+      // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
+      const bool cd = (cmask >> ((r - (P - p)) & 63)) & 1ull;
+      dg = q.c0 + clamp_nugget(nv * (1.0 - (cd ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
+    }
+  }
+  __syncwarp();
+  const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
+  switch (q.cov) {
+    case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
+    case COV_M15: ws_pair_stage<COV_M15, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
+    case COV_M25: ws_pair_stage<COV_M25, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
+    default: ws_pair_stage<COV_ESQE, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
+  }
+  if (r < P) buf[tri_col(r, P)] = dg;
+}
+
+template <int P, int D>
+__global__ void __launch_bounds__(kWsThreads, 1)
+u_band_ws_kernel(const UParams q) {
+  constexpr int G = 8;
+  using LY = BandLayout<G, P, D>;
+  using WL = WsLayout<P, D>;
+  constexpr int NB = LY::NB;
+  constexpr int S0 = LY::S0, S1 = LY::S1, S2 = LY::S2, S3 = LY::S3;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned GMASK = (1u << G) - 1u;
+  constexpr int kSelfLane = band_owner<G>(P - 1);
+
+#ifdef GPV_SIMT_EMU
+  double* smem = emu_dynamic_smem();
+#else
+  extern __shared__ __align__(16) double smem[];
+#endif
+  __shared__ double etab[64];
+  __shared__ int full_cnt[kWsConsumerWarps][kWsSlots][4];   // how many times set `sub` of the slot has been filled
+  __shared__ int empty_cnt[kWsConsumerWarps][kWsSlots];     // how many times the slot has been consumed
+  __shared__ double red[kWsConsumerWarps][4];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int d = (D > 0) ? D : q.d;
+  const int p = q.p;
+  if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+  if (threadIdx.x < kWsConsumerWarps * kWsSlots * 4) (&full_cnt[0][0][0])[threadIdx.x] = 0;
+  if (threadIdx.x < kWsConsumerWarps * kWsSlots) (&empty_cnt[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+
+  // set buffer (consumer c, slot s, set sub): triangle then its input stage; the skew keeps the broadcast words
+  // of the four sets of a consumer instruction in different banks (as in u_band_kernel)
+  auto set_buf = [&](int c, int s, int sub) -> double* {
+    return smem + (size_t)((c * kWsSlots + s) * 4 + sub) * WL::kSet + ((sub & 1) * 8 + (sub >> 1) * 4);
+  };
+  const int64_t stride = (int64_t)gridDim.x * WL::kSetsPerBlock;
+
+  double acc_quad = 0.0, acc_logd = 0.0, acc_qden = 0.0, acc_lden = 0.0;
+  if (warp < kWsConsumerWarps) {
+    // ================================ consumer ================================
+    ws_regs_inc<kWsConsumerRegs>();
+    const int c = warp;
+    const int sub = lane / G;
+    const int gl = lane % G;
+    const int base = sub * G;
+    int rc[NB];
+    bool vb[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int r = band_row<G>(b, gl);
+      vb[b] = r < P;
+      rc[b] = vb[b] ? r : P - 1;
+    }
+    const int64_t first = ((int64_t)blockIdx.x * kWsConsumerWarps + c) * 4;
+    int k = 0;
+    for (int64_t s0 = first; s0 < q.nsets; s0 += stride, ++k) {
+      const int slot = k & 1;
+      const int fill = (k >> 1) + 1;
+      if (lane < 4) ws_wait(&full_cnt[c][slot][lane], fill);
+      __syncwarp();
+      double* buf = set_buf(c, slot, sub);
+      double* st = buf + LY::kBuf;
+      const uint64_t cmask = reinterpret_cast<const unsigned long long*>(st + LY::kOffMeta)[0];
+      const int row = reinterpret_cast<const int*>(st + LY::kOffMeta + 1)[0];
+      const int n0 = reinterpret_cast<const int*>(st + LY::kOffMeta + 1)[1];
+      const bool row_ok = row >= 0;
+      const int npad = P - n0;
+      const int* ids = reinterpret_cast<const int*>(st + LY::kOffIds);
+      const double* nugs = st + LY::kOffNug;
+      int id[NB];
+      bool cd[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        id[b] = vb[b] ? ids[rc[b]] : -1;
+        cd[b] = (id[b] >= 0) ? (bool)((cmask >> ((rc[b] - (P - p)) & 63)) & 1ull) : false;
+      }
+#include "u_band_factor.inc"
+      __syncwarp();
+      if (lane == 0) ws_signal(&empty_cnt[c][slot], fill);
+    }
+  } else {
+    // ================================ producer ================================
+    ws_regs_dec<kWsProducerRegs>();
+    const int pw = warp - kWsConsumerWarps;
+    const int c = pw >> 1;
+    const int h = pw & 1;
+    const int64_t first = ((int64_t)blockIdx.x * kWsConsumerWarps + c) * 4;
+    int k = 0;
+    for (int64_t s0 = first; s0 < q.nsets; s0 += stride, ++k) {
+      const int slot = k & 1;
+      const int fill = (k >> 1) + 1;
+      if (k >= kWsSlots) {                       // the consumer has finished the previous use of this slot
+        if (lane == 0) ws_wait(&empty_cnt[c][slot], fill - 1);
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int e = 0; e < 2; ++e) {
+        const int sub = 2 * h + e;
+        double* buf = set_buf(c, slot, sub);
+        ws_produce_set<P, D>(q, s0 + sub, buf, buf + LY::kBuf, etab, lane, d, p);
+        __syncwarp();
+        if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
+      }
+    }
+  }
+
+  // ---- deterministic block reduction of the likelihood partial sums (consumer warps hold them) -------------
+  if (q.partials != nullptr) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      acc_quad += __shfl_xor_sync(FULL, acc_quad, o);
+      acc_logd += __shfl_xor_sync(FULL, acc_logd, o);
+      acc_qden += __shfl_xor_sync(FULL, acc_qden, o);
+      acc_lden += __shfl_xor_sync(FULL, acc_lden, o);
+    }
+    if (lane == 0 && warp < kWsConsumerWarps) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; red[warp][2] = acc_qden; red[warp][3] = acc_lden; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double a = 0.0;
+      for (int w = 0; w < kWsConsumerWarps; ++w) a += red[w][threadIdx.x];
+      q.partials[4 * blockIdx.x + threadIdx.x] = a;
+    }
+  }
+}
+
+}  // namespace gpv

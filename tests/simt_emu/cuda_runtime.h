@@ -13,6 +13,7 @@
 // oracle without a GPU; timing, register allocation and the real memory model are not modelled.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 #include <cmath>
 #include <cstdint>
 #include <cstring>

@@ -6,6 +6,7 @@
 #include "cuda_runtime.h"   // the stand-in (this directory comes first on the include path)
 #include "bessel_table.cuh"
 #include "u_band.cuh"
+#include "u_band_ws.cuh"
 
 #include <cstdlib>
 #include <thread>
@@ -60,6 +61,10 @@ template <int G, int P, int D>
 void run_sets(int grid, const gpv::UParams& q) {
   run_grid(gpv::u_sets_kernel<G, P, D, false>, grid, gpv::kThreadsPerBlock, gpv::SetLayout<G, P, D>::kBytesPerBlock, q);
 }
+template <int P, int D>
+void run_ws(int grid, const gpv::UParams& q) {
+  run_grid(gpv::u_band_ws_kernel<P, D>, grid, gpv::kWsThreads, gpv::WsLayout<P, D>::kBytesPerBlock, q);
+}
 template <int G, int P, int D>
 void run_band(int grid, const gpv::UParams& q) {
   run_grid(gpv::u_band_kernel<G, P, D, false>, grid, gpv::kThreadsPerBlock, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
@@ -75,7 +80,12 @@ void run_band(int grid, const gpv::UParams& q) {
 // family 1 = u_band_kernel (three or four rows per lane), family 0 = u_sets_kernel (two rows per lane; D = 0 is
 // the run-time-dimension instantiation).
 static int emu_launch(int family, int G, int P, int D, int grid, const gpv::UParams& q) {
-  if (family == 1) {
+  if (family == 2) {            // warp-specialised experiment (u_band_ws.cuh)
+    if (P == 31 && D == 2) run_ws<31, 2>(grid, q);
+    else if (P == 32 && D == 3) run_ws<32, 3>(grid, q);
+    else if (P == 26 && D == 2) run_ws<26, 2>(grid, q);
+    else return 1;
+  } else if (family == 1) {
     if (G == 8 && P == 31 && D == 2) run_band<8, 31, 2>(grid, q);
     else if (G == 8 && P == 21 && D == 3) run_band<8, 21, 3>(grid, q);
     else if (G == 16 && P == 41 && D == 3) run_band<16, 41, 3>(grid, q);

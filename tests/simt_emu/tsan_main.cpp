@@ -9,12 +9,12 @@
 #include <random>
 #include <vector>
 
-extern "C" int emu_u_band(int G, int P, int D, int grid, int64_t nsets, int p, int d, const double* locs,
+extern "C" int emu_u_sets(int family, int G, int P, int D, int grid, int64_t nsets, int p, int d, const double* locs,
                           const int32_t* nn, const uint64_t* cond, const double* nuggets, double* out,
                           const int64_t* row_off, const double* zloc, int full_z, double* partials,
                           unsigned long long* nfail, long long* first_fail, int cov, const double* c);
 
-static int run(int G, int P, int d, int n) {
+static int run(int family, int G, int P, int d, int n) {
   const int p = P;
   std::mt19937_64 rng(11);
   std::uniform_real_distribution<double> U(0.0, 1.0);
@@ -31,16 +31,18 @@ static int run(int G, int P, int d, int n) {
   unsigned long long nfail = 0;
   long long first = INT64_MAX;
   const double c[5] = {1.0, std::sqrt(3.0) / 0.3, 0, 0, 0};
-  const int rc = emu_u_band(G, P, d, 2, n, p, d, locs.data(), nn.data(), cond.data(), nug.data(), out.data(), nullptr,
+  const int rc = emu_u_sets(family, G, P, d, 2, n, p, d, locs.data(), nn.data(), cond.data(), nug.data(), out.data(), nullptr,
                             z.data(), 1, part.data(), &nfail, &first, 1, c);
   double s = 0;
   for (double v : out) s += v;
-  std::printf("G=%d P=%d d=%d: rc=%d nfail=%llu checksum=%.12g partial0=%.12g\n", G, P, d, rc, nfail, s, part[0] + part[4]);
+  std::printf("family=%d G=%d P=%d d=%d: rc=%d nfail=%llu checksum=%.12g partial0=%.12g\n", family, G, P, d, rc, nfail, s, part[0] + part[4]);
   return rc != 0 || nfail != 0 || !(s == s);
 }
 
 int main() {
-  int bad = run(8, 31, 2, 70);
-  bad |= run(16, 41, 3, 40);
+  int bad = run(1, 8, 31, 2, 70);
+  bad |= run(1, 16, 41, 3, 40);
+  bad |= run(0, 16, 31, 2, 40);    // two-row kernel
+  bad |= run(2, 8, 31, 2, 100);    // warp-specialised experiment: slot hand-over between producer and consumer warps
   return bad;
 }

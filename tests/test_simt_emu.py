@@ -272,3 +272,31 @@ def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
         scale = np.abs(Lr[ok]).max(axis=1, keepdims=True)
         assert (np.abs(got[ok] - Lr[ok]) / scale).max() < 1e-9, trial
         assert np.all(got[failed] == 0)
+
+
+@pytest.mark.parametrize("P,m,d,covType,cp", [
+    (31, 30, 2, "matern", [1.3, 0.25, 1.5]),
+    (31, 26, 2, "esqe", [0.7, 0.3, 0.4, 0.2]),          # p = 27 < P = 31
+    (32, 31, 3, "matern", [1.0, 0.5, 2.5]),             # even P: the half iteration t = P/2
+    (26, 25, 2, "matern", [1.0, 0.3, 0.5]),
+])
+def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp):
+    """u_band_ws.cuh (producer warps fill the staged triangle warp-per-set, consumer warps run the shared
+    factorisation text): values against the oracle, zero fill, fused sums, a ragged tail, slot reuse over
+    several passes; and for P = 31, d = 2 bit-identical to u_band_kernel (same arithmetic per pair)."""
+    L = _build(emu_dir)
+    n = 150                                   # 2 blocks x 16 sets per pass: five passes per block, slots reused
+    locs, revNN, rcf = _problem(n, m, d, seed=P * 7 + m, p_drop=0.1 if P == 31 and m == 26 else 0.0)
+    nug = np.random.default_rng(1).uniform(0.05, 0.15, n)
+    z = np.random.default_rng(2).standard_normal(n)
+    ref = _oracle(locs, revNN, rcf, nug, covType, cp)
+    got, partials, nfail, _, n0 = _run(L, 8, P, locs, revNN, rcf, nug, covType, cp, z=z, family=2)
+    got = got.reshape(n, m + 1)
+    Lr = ref["Lentries"]
+    assert nfail == 0 and not np.isnan(got).any()
+    assert np.array_equal(got == 0, Lr == 0)
+    assert (np.abs(got - Lr) / np.abs(Lr).max(axis=1, keepdims=True)).max() < 1e-10
+    if P == 31 and d == 2:
+        base, pb, _, _, _ = _run(L, 8, 31, locs, revNN, rcf, nug, covType, cp, z=z, family=1)
+        assert np.array_equal(base.reshape(n, m + 1), got)
+        assert np.allclose(partials.reshape(-1, 4).sum(axis=0), pb.reshape(-1, 4).sum(axis=0), rtol=1e-13, atol=0)
