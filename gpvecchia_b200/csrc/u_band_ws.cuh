@@ -101,8 +101,13 @@ static __device__ __noinline__ void ws_pair_stage(CovConsts cc, double* __restri
   }
 }
 
+// id of entry `lane` of set sidx as stored (-1: missing, past the row, or past the last set)
+__device__ __forceinline__ int ws_load_raw(const UParams& q, int64_t sidx, int lane, int p) {
+  return (sidx < q.nsets && lane < p) ? q.nn[sidx * (int64_t)p + lane] : -1;
+}
+
 template <int P, int D>
-__device__ __forceinline__ void ws_produce_set(const UParams& q, int64_t sidx, double* __restrict__ buf,
+__device__ __forceinline__ void ws_produce_set(const UParams& q, int64_t sidx, int raw, double* __restrict__ buf,
                                                double* __restrict__ st, const double* __restrict__ etab,
                                                int lane, int d, int p) {
   using LY = BandLayout<8, P, D>;
@@ -116,7 +121,6 @@ __device__ __forceinline__ void ws_produce_set(const UParams& q, int64_t sidx, d
   const bool live = sidx < q.nsets;
   // ids of the row as stored, compaction like inds.elem(find(inds)) (U_NZentries.cpp:41-45): missing entries
   // become LEADING padding
-  const int raw = (live && lane < p) ? q.nn[sidx * (int64_t)p + lane] : -1;
   const unsigned bal = __ballot_sync(FULL, raw >= 0);
   const int n0 = __popc(bal);
   const int npad = P - n0;
@@ -260,6 +264,7 @@ u_band_ws_kernel(const UParams q) {
     const int h = pw & 1;
     const int64_t first = ((int64_t)blockIdx.x * kWsConsumerWarps + c) * 4;
     int k = 0;
+    int raw = ws_load_raw(q, first + 2 * h, lane, p);        // ids of the next set travel during the pair stage
     for (int64_t s0 = first; s0 < q.nsets; s0 += stride, ++k) {
       const int slot = k & 1;
       const int fill = (k >> 1) + 1;
@@ -271,7 +276,9 @@ u_band_ws_kernel(const UParams q) {
       for (int e = 0; e < 2; ++e) {
         const int sub = 2 * h + e;
         double* buf = set_buf(c, slot, sub);
-        ws_produce_set<P, D>(q, s0 + sub, buf, buf + LY::kBuf, etab, lane, d, p);
+        const int raw_cur = raw;
+        raw = ws_load_raw(q, (e == 0) ? s0 + sub + 1 : s0 + stride + 2 * h, lane, p);
+        ws_produce_set<P, D>(q, s0 + sub, raw_cur, buf, buf + LY::kBuf, etab, lane, d, p);
         __syncwarp();
         if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
       }
