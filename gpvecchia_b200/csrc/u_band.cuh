@@ -367,6 +367,7 @@ u_band_kernel(const UParams q) {
     __syncwarp();
 
 #include "u_band_factor.inc"
+#include "u_band_finish.inc"
     __pipeline_wait_prior(0);                              // set i+1 staged, ids of set i+2 landed
     __syncwarp();
     n0 = n0_next;

@@ -28,6 +28,13 @@ constexpr int kWsProducerWarps = 8;
 constexpr int kWsThreads = 32 * (kWsConsumerWarps + kWsProducerWarps);
 constexpr int kWsSlots = 2;                      // batches in flight per consumer warp
 constexpr int kWsConsumerRegs = 240, kWsProducerRegs = 96;
+// GPV_WS_FINISH_IN_PRODUCERS = 1: the consumers stop after the factorisation (steps 4-5) and the producer warps
+// run the sweep and the outputs (steps 6-7: u_band_finish.inc) as a second task, taking turns per batch; a
+// consumer then only loads rows and eliminates.  Everything the sweep needs is in the slot: the unscaled columns,
+// 1 / d_k in the diagonal slots, d_{P-1} in the last one, and the failure flag in the stage's raw-id words.
+#ifndef GPV_WS_FINISH_IN_PRODUCERS
+#define GPV_WS_FINISH_IN_PRODUCERS 0
+#endif
 
 template <int P, int D>
 struct WsLayout {
@@ -196,14 +203,15 @@ u_band_ws_kernel(const UParams q) {
   __shared__ double etab[64];
   __shared__ int full_cnt[kWsConsumerWarps][kWsSlots][4];   // how many times set `sub` of the slot has been filled
   __shared__ int empty_cnt[kWsConsumerWarps][kWsSlots];     // how many times the slot has been consumed
-  __shared__ double red[kWsConsumerWarps][4];
+  __shared__ int fact_cnt[kWsConsumerWarps][kWsSlots];      // how many times the slot has been factored (finish in producers)
+  __shared__ double red[kWsConsumerWarps + kWsProducerWarps][4];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int d = (D > 0) ? D : q.d;
   const int p = q.p;
   if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
   if (threadIdx.x < kWsConsumerWarps * kWsSlots * 4) (&full_cnt[0][0][0])[threadIdx.x] = 0;
-  if (threadIdx.x < kWsConsumerWarps * kWsSlots) (&empty_cnt[0][0])[threadIdx.x] = 0;
+  if (threadIdx.x < kWsConsumerWarps * kWsSlots) { (&empty_cnt[0][0])[threadIdx.x] = 0; (&fact_cnt[0][0])[threadIdx.x] = 0; }
   __syncthreads();
 
   // set buffer (consumer c, slot s, set sub): triangle then its input stage; the skew keeps the broadcast words
@@ -253,8 +261,16 @@ u_band_ws_kernel(const UParams q) {
         cd[b] = (id[b] >= 0) ? (bool)((cmask >> ((rc[b] - (P - p)) & 63)) & 1ull) : false;
       }
 #include "u_band_factor.inc"
+#if GPV_WS_FINISH_IN_PRODUCERS
+      (void)dlast; (void)nugs; (void)row_ok; (void)npad; (void)id; (void)cd;
+      if (gl == 0) reinterpret_cast<int*>(st + LY::kOffRaw)[0] = fail ? 1 : 0;
+      __syncwarp();
+      if (lane == 0) ws_signal(&fact_cnt[c][slot], fill);
+#else
+#include "u_band_finish.inc"
       __syncwarp();
       if (lane == 0) ws_signal(&empty_cnt[c][slot], fill);
+#endif
     }
   } else {
     // ================================ producer ================================
@@ -263,6 +279,45 @@ u_band_ws_kernel(const UParams q) {
     const int c = pw >> 1;
     const int h = pw & 1;
     const int64_t first = ((int64_t)blockIdx.x * kWsConsumerWarps + c) * 4;
+#if GPV_WS_FINISH_IN_PRODUCERS
+    // steps 6-7 of batch kb of consumer c, with the consumer's lane mapping (eight lanes per set, four sets)
+    const int sub_f = lane / G, gl = lane % G, base = sub_f * G;
+    int rc[NB];
+    bool vb[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int r = band_row<G>(b, gl);
+      vb[b] = r < P;
+      rc[b] = vb[b] ? r : P - 1;
+    }
+    auto finish_batch = [&](int kb) {
+      const int slot = kb & 1;
+      const int fill = (kb >> 1) + 1;
+      if (lane == 0) ws_wait(&fact_cnt[c][slot], fill);
+      __syncwarp();
+      double* buf = set_buf(c, slot, sub_f);
+      double* st = buf + LY::kBuf;
+      const uint64_t cmask = reinterpret_cast<const unsigned long long*>(st + LY::kOffMeta)[0];
+      const int row = reinterpret_cast<const int*>(st + LY::kOffMeta + 1)[0];
+      const int n0 = reinterpret_cast<const int*>(st + LY::kOffMeta + 1)[1];
+      const bool row_ok = row >= 0;
+      const int npad = P - n0;
+      const int* ids = reinterpret_cast<const int*>(st + LY::kOffIds);
+      const double* nugs = st + LY::kOffNug;
+      int id[NB];
+      bool cd[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        id[b] = vb[b] ? ids[rc[b]] : -1;
+        cd[b] = (id[b] >= 0) ? (bool)((cmask >> ((rc[b] - (P - p)) & 63)) & 1ull) : false;
+      }
+      const bool fail = reinterpret_cast<const int*>(st + LY::kOffRaw)[0] != 0;
+      const double dlast = buf[tri_col(P - 1, P)];
+#include "u_band_finish.inc"
+      __syncwarp();
+      if (lane == 0) ws_signal(&empty_cnt[c][slot], fill);
+    };
+#endif
     int k = 0;
     int raw = ws_load_raw(q, first + 2 * h, lane, p);        // ids of the next set travel during the pair stage
     for (int64_t s0 = first; s0 < q.nsets; s0 += stride, ++k) {
@@ -282,10 +337,16 @@ u_band_ws_kernel(const UParams q) {
         __syncwarp();
         if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
       }
+#if GPV_WS_FINISH_IN_PRODUCERS
+      if (k >= 1 && ((k - 1) & 1) == h) finish_batch(k - 1);
+#endif
     }
+#if GPV_WS_FINISH_IN_PRODUCERS
+    if (k >= 1 && ((k - 1) & 1) == h) finish_batch(k - 1);       // the last batch(es) of this consumer
+#endif
   }
 
-  // ---- deterministic block reduction of the likelihood partial sums (consumer warps hold them) -------------
+  // ---- deterministic block reduction of the likelihood partial sums (held by the warps that run step 7) ------
   if (q.partials != nullptr) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -294,11 +355,11 @@ u_band_ws_kernel(const UParams q) {
       acc_qden += __shfl_xor_sync(FULL, acc_qden, o);
       acc_lden += __shfl_xor_sync(FULL, acc_lden, o);
     }
-    if (lane == 0 && warp < kWsConsumerWarps) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; red[warp][2] = acc_qden; red[warp][3] = acc_lden; }
+    if (lane == 0) { red[warp][0] = acc_quad; red[warp][1] = acc_logd; red[warp][2] = acc_qden; red[warp][3] = acc_lden; }
     __syncthreads();
     if (threadIdx.x < 4) {
       double a = 0.0;
-      for (int w = 0; w < kWsConsumerWarps; ++w) a += red[w][threadIdx.x];
+      for (int w = 0; w < kWsConsumerWarps + kWsProducerWarps; ++w) a += red[w][threadIdx.x];
       q.partials[4 * blockIdx.x + threadIdx.x] = a;
     }
   }

@@ -218,7 +218,7 @@ def test_early_reciprocal_experiment_is_bit_identical(emu_dir):
     assert fa == fb and ia == ib and np.array_equal(a, b, equal_nan=True)
 
 
-@pytest.mark.parametrize("defs", [(), ("GPV_BAND_EARLY_RCP=1",)])
+@pytest.mark.parametrize("defs", [(), ("GPV_BAND_EARLY_RCP=1",), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
 def test_shared_memory_protocol_is_race_free_under_thread_sanitizer(tmp_path, defs):
     """One host thread per CUDA thread, barriers only where the kernel synchronises: an exchange through shared
     memory that no __syncwarp / __syncthreads orders is a data race ThreadSanitizer reports (tests/simt_emu/
@@ -280,11 +280,13 @@ def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
     (32, 31, 3, "matern", [1.0, 0.5, 2.5]),             # even P: the half iteration t = P/2
     (26, 25, 2, "matern", [1.0, 0.3, 0.5]),
 ])
-def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp):
+@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
+def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp, defs):
     """u_band_ws.cuh (producer warps fill the staged triangle warp-per-set, consumer warps run the shared
     factorisation text): values against the oracle, zero fill, fused sums, a ragged tail, slot reuse over
-    several passes; and for P = 31, d = 2 bit-identical to u_band_kernel (same arithmetic per pair)."""
-    L = _build(emu_dir)
+    several passes; and for P = 31, d = 2 bit-identical to u_band_kernel (same arithmetic per pair).  Second
+    build: the producers also run the sweep and the outputs (GPV_WS_FINISH_IN_PRODUCERS)."""
+    L = _build(emu_dir, defs)
     n = 150                                   # 2 blocks x 16 sets per pass: five passes per block, slots reused
     locs, revNN, rcf = _problem(n, m, d, seed=P * 7 + m, p_drop=0.1 if P == 31 and m == 26 else 0.0)
     nug = np.random.default_rng(1).uniform(0.05, 0.15, n)
