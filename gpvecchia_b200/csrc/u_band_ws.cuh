@@ -113,66 +113,93 @@ __device__ __forceinline__ int ws_load_raw(const UParams& q, int64_t sidx, int l
   return (sidx < q.nsets && lane < p) ? q.nn[sidx * (int64_t)p + lane] : -1;
 }
 
+// What a producer lane knows about point `lane` of a set before the set's buffer is free: gathered one set ahead,
+// so the loads travel while the previous set's pair stage runs.
+template <int DD>
+struct WsPoint {
+  int id, n0, rowv;
+  unsigned long long cmask;     // lane 0 only
+  double x[DD], nv, zv;
+};
+
+// ids of the row as stored -> compaction like inds.elem(find(inds)) (U_NZentries.cpp:41-45; missing entries become
+// LEADING padding) through the warp's scratch words -> coordinates, nugget and z of point `lane` (loads issued
+// here, consumed by ws_fill_set)
 template <int P, int D>
-__device__ __forceinline__ void ws_produce_set(const UParams& q, int64_t sidx, int raw, double* __restrict__ buf,
-                                               double* __restrict__ st, const double* __restrict__ etab,
-                                               int lane, int d, int p) {
+__device__ __forceinline__ WsPoint<BandLayout<8, P, D>::DD> ws_gather_set(const UParams& q, int64_t sidx, int raw,
+                                                                           int* __restrict__ scratch, int lane, int d) {
   using LY = BandLayout<8, P, D>;
   constexpr unsigned FULL = 0xffffffffu;
+  WsPoint<LY::DD> pt;
+  const bool live = sidx < q.nsets;
+  const unsigned bal = __ballot_sync(FULL, raw >= 0);
+  pt.n0 = __popc(bal);
+  const int npad = P - pt.n0;
+  __syncwarp();                                   // the previous set's reads of the scratch words are done
+  scratch[lane] = -1;
+  __syncwarp();
+  if (raw >= 0) scratch[npad + __popc(bal & ((1u << lane) - 1u))] = raw;
+  __syncwarp();
+  pt.id = (lane < P) ? scratch[lane] : -1;
+  pt.cmask = 0ull;
+  pt.rowv = -1;
+  if (lane == 0 && live) {
+    pt.cmask = (unsigned long long)q.cond[sidx];
+    pt.rowv = (q.rowmap != nullptr) ? q.rowmap[sidx] : (int)(q.set_base + sidx);
+  }
+#pragma unroll
+  for (int c = 0; c < LY::DD; ++c) pt.x[c] = 0.0;
+  pt.nv = 0.0; pt.zv = 0.0;
+  if (pt.id >= 0) {
+#pragma unroll
+    for (int c = 0; c < LY::DD; ++c)
+      if (c < d) pt.x[c] = q.locs[(int64_t)pt.id * d + c];
+    pt.nv = q.nuggets[pt.id];
+    if (q.zloc != nullptr) pt.zv = q.zloc[pt.id];
+  }
+  return pt;
+}
+
+// input stage, staged triangle, diagonal and padding of one set from its gathered points
+template <int P, int D>
+__device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<BandLayout<8, P, D>::DD>& pt,
+                                            double* __restrict__ buf, double* __restrict__ st,
+                                            const double* __restrict__ etab, int lane, int d, int p) {
+  using LY = BandLayout<8, P, D>;
   int* ids = reinterpret_cast<int*>(st + LY::kOffIds);
   double* xs = st;
   double* nug = st + LY::kOffNug;
   double* zs = st + LY::kOffZ;
   double* meta = st + LY::kOffMeta;
   int* metai = reinterpret_cast<int*>(meta + 1);
-  const bool live = sidx < q.nsets;
-  // ids of the row as stored, compaction like inds.elem(find(inds)) (U_NZentries.cpp:41-45): missing entries
-  // become LEADING padding
-  const unsigned bal = __ballot_sync(FULL, raw >= 0);
-  const int n0 = __popc(bal);
-  const int npad = P - n0;
-  if (lane < npad && lane < P) ids[lane] = -1;
-  __syncwarp();
-  if (raw >= 0) ids[npad + __popc(bal & ((1u << lane) - 1u))] = raw;
-  unsigned long long cmask = 0ull;
+  const int npad = P - pt.n0;
   if (lane == 0) {
-    cmask = live ? (unsigned long long)q.cond[sidx] : 0ull;
-    reinterpret_cast<unsigned long long*>(meta)[0] = cmask;
-    metai[0] = live ? (q.rowmap != nullptr ? q.rowmap[sidx] : (int)(q.set_base + sidx)) : -1;
-    metai[1] = n0;
+    reinterpret_cast<unsigned long long*>(meta)[0] = pt.cmask;
+    metai[0] = pt.rowv;
+    metai[1] = pt.n0;
   }
-  __syncwarp();
-  cmask = reinterpret_cast<const unsigned long long*>(meta)[0];
-  // point r = lane of the compacted set
-  const int r = lane;
-  const int id = (r < P) ? ids[r] : -1;
+  const int r = lane;                 // point r = lane of the compacted set
   double x[LY::DD];
 #pragma unroll
-  for (int c = 0; c < LY::DD; ++c) x[c] = 0.0;
-  double nv = 0.0, zv = 0.0;
-  if (id >= 0) {
-#pragma unroll
-    for (int c = 0; c < LY::DD; ++c)
-      if (c < d) x[c] = q.locs[(int64_t)id * d + c];
-    nv = q.nuggets[id];
-    if (q.zloc != nullptr) zv = q.zloc[id];
-  }
-  double dg = 1.0;
+  for (int c = 0; c < LY::DD; ++c) x[c] = pt.x[c];
   if (r < P) {
+    ids[r] = pt.id;
     if (D == 2) {
       reinterpret_cast<double2*>(xs)[r] = make_double2(x[0], x[1]);
     } else {
       for (int c = 0; c < d; ++c) xs[c * LY::PX + r] = x[c];
     }
-    nug[r] = nv;
-    zs[r] = zv;
-    if (id >= 0) {
-      // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
-      const bool cd = (cmask >> ((r - (P - p)) & 63)) & 1ull;
-      dg = q.c0 + clamp_nugget(nv * (1.0 - (cd ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
-    }
+    nug[r] = pt.nv;
+    zs[r] = pt.zv;
   }
   __syncwarp();
+  const unsigned long long cmask = reinterpret_cast<const unsigned long long*>(meta)[0];
+  double dg = 1.0;
+  if (r < P && pt.id >= 0) {
+    // compacted entry j reads revCond[row, p - n0 + j] (:47); local index = npad + j
+    const bool cd = (cmask >> ((r - (P - p)) & 63)) & 1ull;
+    dg = q.c0 + clamp_nugget(pt.nv * (1.0 - (cd ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
+  }
   const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
   switch (q.cov) {
     case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
@@ -205,6 +232,7 @@ u_band_ws_kernel(const UParams q) {
   __shared__ int empty_cnt[kWsConsumerWarps][kWsSlots];     // how many times the slot has been consumed
   __shared__ int fact_cnt[kWsConsumerWarps][kWsSlots];      // how many times the slot has been factored (finish in producers)
   __shared__ double red[kWsConsumerWarps + kWsProducerWarps][4];
+  __shared__ int pscratch[kWsProducerWarps][32];            // compaction scratch of each producer warp
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int d = (D > 0) ? D : q.d;
@@ -318,22 +346,29 @@ u_band_ws_kernel(const UParams q) {
       if (lane == 0) ws_signal(&empty_cnt[c][slot], fill);
     };
 #endif
+    // The producer's sets in order: j = 2 k + e is set 2 h + e of the consumer's batch k.  One set ahead of the one
+    // being filled, the next set's points are gathered (loads in flight during the pair stage); two ahead, its ids.
+    auto sidx_of = [&](int j) -> int64_t { return first + (int64_t)(j >> 1) * stride + 2 * h + (j & 1); };
+    int* scratch = &pscratch[pw][0];
+    int raw = ws_load_raw(q, sidx_of(1), lane, p);
+    WsPoint<LY::DD> pt = ws_gather_set<P, D>(q, sidx_of(0), ws_load_raw(q, sidx_of(0), lane, p), scratch, lane, d);
     int k = 0;
-    int raw = ws_load_raw(q, first + 2 * h, lane, p);        // ids of the next set travel during the pair stage
     for (int64_t s0 = first; s0 < q.nsets; s0 += stride, ++k) {
       const int slot = k & 1;
       const int fill = (k >> 1) + 1;
-      if (k >= kWsSlots) {                       // the consumer has finished the previous use of this slot
+      if (k >= kWsSlots) {                       // the previous use of this slot has been consumed
         if (lane == 0) ws_wait(&empty_cnt[c][slot], fill - 1);
         __syncwarp();
       }
 #pragma unroll 1
       for (int e = 0; e < 2; ++e) {
+        const int j = 2 * k + e;
         const int sub = 2 * h + e;
         double* buf = set_buf(c, slot, sub);
-        const int raw_cur = raw;
-        raw = ws_load_raw(q, (e == 0) ? s0 + sub + 1 : s0 + stride + 2 * h, lane, p);
-        ws_produce_set<P, D>(q, s0 + sub, raw_cur, buf, buf + LY::kBuf, etab, lane, d, p);
+        const WsPoint<LY::DD> cur = pt;
+        pt = ws_gather_set<P, D>(q, sidx_of(j + 1), raw, scratch, lane, d);
+        raw = ws_load_raw(q, sidx_of(j + 2), lane, p);
+        ws_fill_set<P, D>(q, cur, buf, buf + LY::kBuf, etab, lane, d, p);
         __syncwarp();
         if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
       }
@@ -342,7 +377,7 @@ u_band_ws_kernel(const UParams q) {
 #endif
     }
 #if GPV_WS_FINISH_IN_PRODUCERS
-    if (k >= 1 && ((k - 1) & 1) == h) finish_batch(k - 1);       // the last batch(es) of this consumer
+    if (k >= 1 && ((k - 1) & 1) == h) finish_batch(k - 1);       // the consumer's last batch
 #endif
   }
 
