@@ -280,7 +280,7 @@ def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
     (32, 31, 3, "matern", [1.0, 0.5, 2.5]),             # even P: the half iteration t = P/2
     (26, 25, 2, "matern", [1.0, 0.3, 0.5]),
 ])
-@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
+@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",), ("GPV_WS_FINISH_IN_PRODUCERS=1", "GPV_BAND_EARLY_RCP=1")])
 def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp, defs):
     """u_band_ws.cuh (producer warps fill the staged triangle warp-per-set, consumer warps run the shared
     factorisation text): values against the oracle, zero fill, fused sums, a ragged tail, slot reuse over
