@@ -77,33 +77,45 @@ template <int REGS> __device__ __forceinline__ void ws_regs_dec() {
 // ---- producer: one set by one warp -------------------------------------------------------------------------
 // Pairs of point r = lane: (r, r + t mod P), t = 1..P/2 (for even P the last t only for r < P/2): every unordered
 // pair once, 15 or 16 per lane.  Four values of t per trip give the lane four independent covariance chains.
+// Where pair (r, t) goes in the packed staged triangle and who the partner is depends only on (r, t): a per-block
+// table holds the offset (in doubles; 0xffff: inactive, the store goes to the lane's dump word) and the partner.
+constexpr int kWsTrips = 4;                       // trips of four pairs: t = 1..16 covers P/2 <= 16
+template <int P>
+__device__ __forceinline__ void ws_build_pair_table(unsigned* __restrict__ wtab) {
+  constexpr int T = P / 2;
+  for (int idx = threadIdx.x; idx < kWsTrips * 4 * 32; idx += blockDim.x) {
+    const int t = idx / 32 + 1, r = idx % 32;
+    const int rr = r < P ? r : P - 1;
+    const int tt = t <= T ? t : T;
+    int j = rr + tt; if (j >= P) j -= P;
+    const bool act = (r < P) && (t <= T) && (2 * t < P || r < P / 2);
+    const int a = rr > j ? rr : j, b = rr > j ? j : rr;
+    wtab[idx] = (act ? (unsigned)(tri_col(b, P) + a - b) : 0xffffu) | ((unsigned)j << 16);
+  }
+}
 template <int KIND, int P, int D>
 static __device__ __noinline__ void ws_pair_stage(CovConsts cc, double* __restrict__ buf, const double* __restrict__ xs,
-                                                  const double (&x)[BandLayout<8, P, D>::DD], int r, int npad,
+                                                  const double (&x)[BandLayout<8, P, D>::DD], int lane,
+                                                  const unsigned* __restrict__ wtab, double* __restrict__ dump,
                                                   const double* __restrict__ etab, int d) {
   using LY = BandLayout<8, P, D>;
-  constexpr int T = LY::kT;
   const double guard = kMathC[7];
-  const int rr = r < P ? r : P - 1;
+  const unsigned* wl = wtab + lane;
 #pragma unroll 1
-  for (int t0 = 1; t0 <= T; t0 += 4) {
+  for (int trip = 0; trip < kWsTrips; ++trip) {
     double r2[4], v[4];
-    int off[4];
+    unsigned ent[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int t = (t0 + u <= T) ? t0 + u : T;
-      int j = rr + t; if (j >= P) j -= P;
-      const bool act = (r < P) && (t0 + u <= T) && (2 * t < P || r < P / 2);
-      const int a = rr > j ? rr : j, b = rr > j ? j : rr;
-      // a pair that involves a padding point (leading indices < npad) is a zero of the identity block
-      off[u] = act ? ((b < npad) ? -2 - (tri_col(b, P) + a - b) : tri_col(b, P) + a - b) : -1;
-      r2[u] = pair_r2<D>(xs, LY::PX, x, j, d, guard);
+      ent[u] = wl[(trip * 4 + u) * 32];
+      r2[u] = pair_r2<D>(xs, LY::PX, x, (int)(ent[u] >> 16), d, guard);
     }
     cov_eval_n<KIND, 4>(r2, v, cc, etab);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (off[u] >= 0) buf[off[u]] = v[u];
-      else if (off[u] <= -2) buf[-2 - off[u]] = 0.0;
+      const unsigned off = ent[u] & 0xffffu;
+      double* dst = (off != 0xffffu) ? buf + off : dump;
+      *dst = v[u];
     }
   }
 }
@@ -164,6 +176,7 @@ __device__ __forceinline__ WsPoint<BandLayout<8, P, D>::DD> ws_gather_set(const 
 template <int P, int D>
 __device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<BandLayout<8, P, D>::DD>& pt,
                                             double* __restrict__ buf, double* __restrict__ st,
+                                            const unsigned* __restrict__ wtab, double* __restrict__ dump,
                                             const double* __restrict__ etab, int lane, int d, int p) {
   using LY = BandLayout<8, P, D>;
   int* ids = reinterpret_cast<int*>(st + LY::kOffIds);
@@ -202,10 +215,17 @@ __device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<Band
   }
   const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
   switch (q.cov) {
-    case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
-    case COV_M15: ws_pair_stage<COV_M15, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
-    case COV_M25: ws_pair_stage<COV_M25, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
-    default: ws_pair_stage<COV_ESQE, P, D>(cc, buf, xs, x, r, npad, etab, d); break;
+    case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+    case COV_M15: ws_pair_stage<COV_M15, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+    case COV_M25: ws_pair_stage<COV_M25, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+    default: ws_pair_stage<COV_ESQE, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+  }
+  if (npad > 0) {
+    // padding occupies the leading indices: zero columns 0..npad-1 of the staged triangle (only the first m rows
+    // of a data set have padding, so this is rare; npad is warp-uniform)
+    __syncwarp();
+    for (int j = 0; j < npad; ++j)
+      if (r < P && r > j) buf[tri_col(j, P) + r - j] = 0.0;
   }
   if (r < P) buf[tri_col(r, P)] = dg;
 }
@@ -233,11 +253,14 @@ u_band_ws_kernel(const UParams q) {
   __shared__ int fact_cnt[kWsConsumerWarps][kWsSlots];      // how many times the slot has been factored (finish in producers)
   __shared__ double red[kWsConsumerWarps + kWsProducerWarps][4];
   __shared__ int pscratch[kWsProducerWarps][32];            // compaction scratch of each producer warp
+  __shared__ double pdump[kWsProducerWarps][32];            // where a lane's inactive pair slots are stored
+  __shared__ unsigned wtab[kWsTrips * 4 * 32];              // pair table of the producers (ws_build_pair_table)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int d = (D > 0) ? D : q.d;
   const int p = q.p;
   if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+  ws_build_pair_table<P>(wtab);
   if (threadIdx.x < kWsConsumerWarps * kWsSlots * 4) (&full_cnt[0][0][0])[threadIdx.x] = 0;
   if (threadIdx.x < kWsConsumerWarps * kWsSlots) { (&empty_cnt[0][0])[threadIdx.x] = 0; (&fact_cnt[0][0])[threadIdx.x] = 0; }
   __syncthreads();
@@ -368,7 +391,7 @@ u_band_ws_kernel(const UParams q) {
         const WsPoint<LY::DD> cur = pt;
         pt = ws_gather_set<P, D>(q, sidx_of(j + 1), raw, scratch, lane, d);
         raw = ws_load_raw(q, sidx_of(j + 2), lane, p);
-        ws_fill_set<P, D>(q, cur, buf, buf + LY::kBuf, etab, lane, d, p);
+        ws_fill_set<P, D>(q, cur, buf, buf + LY::kBuf, wtab, &pdump[pw][lane], etab, lane, d, p);
         __syncwarp();
         if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
       }
