@@ -242,11 +242,13 @@ def test_shared_memory_protocol_is_race_free_under_thread_sanitizer(tmp_path, de
         assert "ThreadSanitizer: data race" in rb.stderr + rb.stdout
 
 
-def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
+@pytest.mark.parametrize("family,defs", [(1, ()), (2, ()), (2, ("GPV_WS_FINISH_IN_PRODUCERS=1",))])
+def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir, family, defs):
     """Seeded sweep through the emulated band kernel: set sizes p = 17..31 on the P = 31 instantiation, holes
     anywhere, mixed latent / response conditioning, and nuggets that include Inf on response-conditioned
-    neighbours (Vecchia-Laplace's missing data, vecchia_laplace_NR.R:108: that neighbour decouples)."""
-    L = _build(emu_dir)
+    neighbours (Vecchia-Laplace's missing data, vecchia_laplace_NR.R:108: that neighbour decouples).  Run for the
+    default band kernel and for both builds of the warp-specialised experiment."""
+    L = _build(emu_dir, defs)
     rng = np.random.default_rng(20240601)
     for trial in range(6):
         m = int(rng.integers(16, 31))
@@ -263,7 +265,7 @@ def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir):
             nug[rng.integers(0, n, 3)] = np.inf
         cp = [float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.2, 0.6)), float(rng.choice([0.5, 1.5, 2.5]))]
         ref = _oracle(locs, revNN, rcf, nug, "matern", cp, mode=1)
-        got, _, nfail, _, n0 = _run(L, 8, 31, locs, revNN, rcf, nug, "matern", cp)
+        got, _, nfail, _, n0 = _run(L, 8, 31, locs, revNN, rcf, nug, "matern", cp, family=family)
         got = got.reshape(n, p)
         Lr = ref["Lentries"]
         failed = np.array([np.all(Lr[k, :n0[k]] == 0) for k in range(n)])
