@@ -9,11 +9,11 @@
 //   * warps 0-3 (one warp group, `setmaxnreg.inc` to 240 registers): CONSUMERS.  Each owns two batch slots of
 //     four sets and runs steps 4-7 (u_band_factor.inc, the same text u_band_kernel includes) on a slot once
 //     its four sets are marked full, then marks the slot empty.
-//   * warps 4-11 (two warp groups, `setmaxnreg.dec` to 96): PRODUCERS, warp-per-set.  Producers 2c and 2c+1
+//   * warps 4-11 (two warp groups, `setmaxnreg.dec` to 128): PRODUCERS, warp-per-set.  Producers 2c and 2c+1
 //     fill sets {0,1} and {2,3} of consumer c's next slot: ids -> compaction (one ballot) -> coordinates,
 //     nugget, z of point `lane` -> the lane's 15 or 16 pairs (lane, lane + t mod P), four at a time -> staged
 //     triangle, diagonal, padding -> full.
-// 12 warps per SM instead of 8 inside the same register file (4*32*240 + 8*32*96 = 55 296) and shared memory
+// 12 warps per SM instead of 8 inside the same register file (4*32*240 + 8*32*128 = 63 488 of the 64 512 the launch holds) and shared memory
 // (32 set buffers of triangle + one input stage = 176 KB).  Slots are handed over through monotone counters in
 // shared memory (release store by one lane after __syncwarp, acquire spin by one lane before __syncwarp).
 // Results are those of u_band_kernel up to the order of nothing: the same pairs, the same arithmetic per pair,
@@ -27,7 +27,7 @@ constexpr int kWsConsumerWarps = 4;
 constexpr int kWsProducerWarps = 8;
 constexpr int kWsThreads = 32 * (kWsConsumerWarps + kWsProducerWarps);
 constexpr int kWsSlots = 2;                      // batches in flight per consumer warp
-constexpr int kWsConsumerRegs = 240, kWsProducerRegs = 96;
+constexpr int kWsConsumerRegs = 240, kWsProducerRegs = 128;
 // GPV_WS_FINISH_IN_PRODUCERS = 1: the consumers stop after the factorisation (steps 4-5) and the producer warps
 // run the sweep and the outputs (steps 6-7: u_band_finish.inc) as a second task, taking turns per batch; a
 // consumer then only loads rows and eliminates.  Everything the sweep needs is in the slot: the unscaled columns,
