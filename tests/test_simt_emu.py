@@ -20,6 +20,8 @@ from gpvecchia_b200 import harness as H
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIBS = {}
+# the warp-specialised experiment hands slots over through spin-waits: a protocol bug must fail, not hang, the run
+pytestmark = pytest.mark.timeout(600)
 
 
 def _build(tmpdir, defs=()):
