@@ -9,6 +9,7 @@
 #include "gpv_internal.h"
 #include "bessel_table.cuh"
 #include "rgamma_coeffs.h"
+#include "cov_setup.h"
 
 #include <atomic>
 #include <climits>
@@ -824,24 +825,6 @@ extern "C" gpv_status gpv_kernel_time_stats(gpv_handle* h, int reset, int64_t* c
 // ------------------------------------------------------------------------------------------------
 // covariance set-up (per call)
 // ------------------------------------------------------------------------------------------------
-static void nu_constants(double nu, double sig2, CovTable* t) {
-  // Temme's auxiliary functions for |mu| <= 1/2 from the Taylor series of 1/Gamma(1+x)
-  const int nl = (int)(nu + 0.5);
-  const double xmu = nu - nl;
-  const double m2 = xmu * xmu;
-  double g1 = 0.0, g2 = 0.0, pl = 0.0, mi = 0.0;
-  // gam2 = sum_{k even} c_k mu^k ; gam1 = -sum_{k odd} c_k mu^(k-1)
-  for (int k = GPV_RGAMMA_NCOEF - 1; k >= 0; --k) {
-    pl = pl * xmu + kRGammaTaylor[k];
-    mi = mi * (-xmu) + kRGammaTaylor[k];
-  }
-  for (int k = ((GPV_RGAMMA_NCOEF - 1) / 2) * 2; k >= 0; k -= 2) g2 = g2 * m2 + kRGammaTaylor[k];
-  for (int k = ((GPV_RGAMMA_NCOEF - 2) / 2) * 2 + 1; k >= 1; k -= 2) g1 = g1 * m2 + kRGammaTaylor[k];
-  t->nu = nu; t->nl = nl; t->xmu = xmu;
-  t->gam1 = -g1; t->gam2 = g2; t->gampl = pl; t->gammi = mi;
-  t->normcon = sig2 / (std::pow(2.0, nu - 1.0) * std::tgamma(nu));   // Matern.cpp:73
-}
-
 struct CovSetup {
   UParams q;
   bool needs_table = false;
@@ -866,17 +849,7 @@ static gpv_status setup_cov(const char* covType, const double* covparms, int nco
       cs->needs_table = true;
       CovTable& t = q.tab;
       nu_constants(nu, sig2, &t);
-      // table range: the top kTabOctaves octaves of w below the squared bounding-box diagonal
-      double wmax = (w_max > 0.0 && std::isfinite(w_max)) ? w_max : 1.0;
-      const int code_hi = hi32_of(wmax) >> (20 - kTabSubBits);
-      int nint = kTabOctaves * kTabSub;
-      int idx0 = code_hi - nint + 1;
-      const int min_code = 1 << kTabSubBits;            // smallest normal exponent
-      if (idx0 < min_code) { nint -= (min_code - idx0); idx0 = min_code; }
-      t.idx0 = idx0; t.nint = nint; t.sub_bits = kTabSubBits; t.deg = kTabDeg;
-      const double ws = (kTabSSplit * range) * (kTabSSplit * range);
-      const int code_split = hi32_of(ws) >> (20 - kTabSubBits);
-      t.w_split = from_hilo(code_split << (20 - kTabSubBits), 0);
+      general_table_range(range, w_max, &t);
     }
   } else if (std::strcmp(covType, "esqe") == 0) {
     if (ncov < 4) return fail(GPV_ERR_ARG, "esqe needs covparms = (sig2_1, r1, sig2_2, r2)");

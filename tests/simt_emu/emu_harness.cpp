@@ -4,11 +4,14 @@
 //   g++ -std=c++17 -O1 -pthread -shared -fPIC -Itests/simt_emu -Igpvecchia_b200/csrc -Iinclude \
 //       [-DGPV_BAND_EARLY_RCP=1] tests/simt_emu/emu_harness.cpp -o libemu.so
 #include "cuda_runtime.h"   // the stand-in (this directory comes first on the include path)
+#define GPV_DEFINE_TABLE_BUILDER
 #include "bessel_table.cuh"
+#include "cov_setup.h"
 #include "u_band.cuh"
 #include "u_band_ws.cuh"
 
 #include <cstdlib>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -25,14 +28,18 @@ namespace {
 
 typedef void (*KernelFn)(const gpv::UParams);
 
+void run_grid_fn(const std::function<void()>& kernel, int grid, int threads, size_t smem_bytes);
 void run_grid(KernelFn kernel, int grid, int threads, size_t smem_bytes, const gpv::UParams& q) {
+  run_grid_fn([&]() { kernel(q); }, grid, threads, smem_bytes);
+}
+void run_grid_fn(const std::function<void()>& kernel, int grid, int threads, size_t smem_bytes) {
   const int nwarps = threads / 32;
   for (int b = 0; b < grid; ++b) {
     void* mem = nullptr;
     if (posix_memalign(&mem, 128, smem_bytes + 128) != 0) std::abort();
     std::memset(mem, 0xFF, smem_bytes + 128);          // uninitialised shared memory reads as NaN
     g_dyn_smem = static_cast<double*>(mem);
-    std::vector<emu::Warp> warps(nwarps);
+    std::vector<emu::Warp> warps(nwarps > 0 ? nwarps : 1);
     emu::Block blk;
     blk.warps = warps.data();
     pthread_barrier_init(&blk.bar, nullptr, threads);
@@ -46,7 +53,7 @@ void run_grid(KernelFn kernel, int grid, int threads, size_t smem_bytes, const g
         emu::tl_lane = t % 32;
         threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)b;
         blockDim.x = (unsigned)threads; gridDim.x = (unsigned)grid;
-        kernel(q);
+        kernel();
       });
     }
     for (auto& th : pool) th.join();
@@ -64,6 +71,10 @@ void run_sets(int grid, const gpv::UParams& q) {
 template <int P, int D>
 void run_ws(int grid, const gpv::UParams& q) {
   run_grid(gpv::u_band_ws_kernel<P, D>, grid, gpv::kWsThreads, gpv::WsLayout<P, D>::kBytesPerBlock, q);
+}
+template <int G, int P, int D>
+void run_band_general(int grid, const gpv::UParams& q) {
+  run_grid(gpv::u_band_kernel<G, P, D, true>, grid, gpv::kThreadsPerBlock, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
 }
 template <int G, int P, int D>
 void run_band(int grid, const gpv::UParams& q) {
@@ -121,4 +132,31 @@ extern "C" int emu_u_sets(int family, int G, int P, int D, int grid, int64_t nse
                             nfail, first_fail, cov, c);
   g_family = 1;
   return rc;
+}
+
+// General-nu Matern (Matern.cpp:72-83) through the table path: the coefficient table is built by the library's
+// own build_cov_table_kernel (one 32-thread block per interval, emulated like the set kernels) with the host
+// set-up of cov_setup.h, then u_band_kernel<G, P, D, general> runs on it.  w_max: squared bounding-box diagonal.
+extern "C" int emu_u_band_general(int G, int P, int D, int grid, int64_t nsets, int p, int d, const double* locs,
+                                  const int32_t* nn, const uint64_t* cond, const double* nuggets, double* out,
+                                  unsigned long long* nfail, long long* first_fail, double sig2, double range,
+                                  double nu, double w_max) {
+  gpv::UParams q;
+  std::memset(&q, 0, sizeof(q));
+  q.nrows = nsets; q.nsets = nsets; q.p = p; q.d = d;
+  q.locs = locs; q.nn = nn; q.cond = cond; q.nuggets = nuggets; q.out = out;
+  q.nfail = nfail; q.first_fail = first_fail;
+  q.cov = gpv::COV_GENERAL; q.c0 = sig2; q.inv_range = 1.0 / range;
+  gpv::nu_constants(nu, sig2, &q.tab);
+  gpv::general_table_range(range, w_max, &q.tab);
+  std::vector<double> coef((size_t)(gpv::kTabDeg + 1) * gpv::kTabStride, 0.0);
+  q.tab.coef = coef.data();
+  const gpv::CovTable t = q.tab;
+  const double inv_range = q.inv_range;
+  double* cp = coef.data();
+  run_grid_fn([&]() { gpv::build_cov_table_kernel(t, inv_range, cp); }, t.nint, 32, 0);
+  if (G == 8 && P == 31 && D == 2) run_band_general<8, 31, 2>(grid, q);
+  else if (G == 16 && P == 41 && D == 3) run_band_general<16, 41, 3>(grid, q);
+  else return 1;
+  return 0;
 }

@@ -306,3 +306,37 @@ def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp, 
         base, pb, _, _, _ = _run(L, 8, 31, locs, revNN, rcf, nug, covType, cp, z=z, family=1)
         assert np.array_equal(base.reshape(n, m + 1), got)
         assert np.allclose(partials.reshape(-1, 4).sum(axis=0), pb.reshape(-1, 4).sum(axis=0), rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("G,P,m,d,nu", [(8, 31, 30, 2, 0.8), (8, 31, 30, 2, 1.3), (16, 41, 40, 3, 2.2)])
+def test_general_nu_table_path_on_the_host(emu_dir, G, P, m, d, nu):
+    """General-nu Matern (Matern.cpp:72-83): the coefficient table built by the library's own
+    build_cov_table_kernel and read by u_band_kernel<general>, both emulated, against the oracle's
+    std::cyl_bessel_k restatement.  Includes duplicated locations (distance 0 -> sigma^2, :76-77) through the
+    kernel's slow path."""
+    L = _build(emu_dir)
+    L.emu_u_band_general.argtypes = [C.c_int] * 4 + [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_double] * 4
+    L.emu_u_band_general.restype = C.c_int
+    n = 80
+    locs, revNN, rcf = _problem(n, m, d, seed=int(nu * 10) + P)
+    locs[50] = locs[20]                      # a duplicate: zero distance inside the later sets
+    nug = np.random.default_rng(1).uniform(0.05, 0.15, n)
+    cp = [1.4, 0.35, nu]
+    ref = _oracle(locs, revNN, rcf, nug, "matern", cp)
+    p = m + 1
+    nn = np.ascontiguousarray(revNN.astype(np.int32) - 1)
+    cond = np.zeros(n, dtype=np.uint64)
+    for j in range(p):
+        cond |= (np.nan_to_num(rcf[:, j], nan=0.0) == 1.0).astype(np.uint64) << np.uint64(j)
+    out = np.full(n * p, np.nan)
+    nfail = np.zeros(1, dtype=np.uint64)
+    first = np.full(1, np.iinfo(np.int64).max, dtype=np.int64)
+    lr = np.ascontiguousarray(locs)
+    w_max = float(((locs.max(axis=0) - locs.min(axis=0)) ** 2).sum())
+    rc = L.emu_u_band_general(G, P, d, 2, n, p, d, lr.ctypes.data, nn.ctypes.data, cond.ctypes.data, nug.ctypes.data,
+                              out.ctypes.data, nfail.ctypes.data, first.ctypes.data, cp[0], cp[1], cp[2], w_max)
+    assert rc == 0 and int(nfail[0]) == 0 and ref["nfail"] == 0
+    got = out.reshape(n, p)
+    Lr = ref["Lentries"]
+    assert np.array_equal(got == 0, Lr == 0)
+    assert (np.abs(got - Lr) / np.abs(Lr).max(axis=1, keepdims=True)).max() < 1e-10
