@@ -613,7 +613,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     H_TRY(cudaFuncSetAttribute((const void*)entry_gen->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                entry_gen->smem_bytes));
     H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)entry_gen->kernel,
-                                                        kThreadsPerBlock, entry_gen->smem_bytes));
+                                                        entry_gen->threads, entry_gen->smem_bytes));
     if (bps < 1) { free_handle(h); return fail(GPV_ERR_CUDA, "kernel %s does not fit an SM", entry_gen->name); }
     h->max_blocks_gen = h->num_sms * bps;
     if (h->max_blocks_gen > h->max_blocks) h->max_blocks = h->max_blocks_gen;   // sizes d_partials

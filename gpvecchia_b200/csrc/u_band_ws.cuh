@@ -125,6 +125,45 @@ __device__ __forceinline__ int ws_load_raw(const UParams& q, int64_t sidx, int l
   return (sidx < q.nsets && lane < p) ? q.nn[sidx * (int64_t)p + lane] : -1;
 }
 
+// General-nu table path (bessel_table.cuh): one warp vote per trip decides between the table and the per-lane
+// slow path (zero distance, far pairs, arguments outside the table), as in u_band_kernel.  Inlined: the table
+// descriptor lives in the kernel parameters.
+template <int P, int D>
+__device__ __forceinline__ void ws_pair_stage_general(const UParams& q, double* __restrict__ buf,
+                                                      const double* __restrict__ xs,
+                                                      const double (&x)[BandLayout<8, P, D>::DD], int lane,
+                                                      const unsigned* __restrict__ wtab, double* __restrict__ dump,
+                                                      const double* __restrict__ etab, int d) {
+  using LY = BandLayout<8, P, D>;
+  const unsigned* wl = wtab + lane;
+#pragma unroll 1
+  for (int trip = 0; trip < kWsTrips; ++trip) {
+    double r2[4], v[4];
+    unsigned ent[4];
+    int idx[4];
+    bool sp = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ent[u] = wl[(trip * 4 + u) * 32];
+      r2[u] = pair_r2<D>(xs, LY::PX, x, (int)(ent[u] >> 16), d, 0.0);
+      sp |= cov_general_special(r2[u], q.tab, &idx[u]);
+    }
+    if (__any_sync(0xffffffffu, sp)) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = cov_general_slow(r2[u], q, etab);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = cov_general_fast(r2[u], idx[u], q.tab);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned off = ent[u] & 0xffffu;
+      double* dst = (off != 0xffffu) ? buf + off : dump;
+      *dst = v[u];
+    }
+  }
+}
+
 // What a producer lane knows about point `lane` of a set before the set's buffer is free: gathered one set ahead,
 // so the loads travel while the previous set's pair stage runs.
 template <int DD>
@@ -173,7 +212,7 @@ __device__ __forceinline__ WsPoint<BandLayout<8, P, D>::DD> ws_gather_set(const 
 }
 
 // input stage, staged triangle, diagonal and padding of one set from its gathered points
-template <int P, int D>
+template <int P, int D, bool GENERAL>
 __device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<BandLayout<8, P, D>::DD>& pt,
                                             double* __restrict__ buf, double* __restrict__ st,
                                             const unsigned* __restrict__ wtab, double* __restrict__ dump,
@@ -213,12 +252,16 @@ __device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<Band
     const bool cd = (cmask >> ((r - (P - p)) & 63)) & 1ull;
     dg = q.c0 + clamp_nugget(pt.nv * (1.0 - (cd ? 1.0 : 0.0)));   // Inf * 0 = NaN kept
   }
-  const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
-  switch (q.cov) {
-    case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
-    case COV_M15: ws_pair_stage<COV_M15, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
-    case COV_M25: ws_pair_stage<COV_M25, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
-    default: ws_pair_stage<COV_ESQE, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+  if (GENERAL) {
+    ws_pair_stage_general<P, D>(q, buf, xs, x, lane, wtab, dump, etab, d);
+  } else {
+    const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
+    switch (q.cov) {
+      case COV_EXP: ws_pair_stage<COV_EXP, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+      case COV_M15: ws_pair_stage<COV_M15, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+      case COV_M25: ws_pair_stage<COV_M25, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+      default: ws_pair_stage<COV_ESQE, P, D>(cc, buf, xs, x, lane, wtab, dump, etab, d); break;
+    }
   }
   if (npad > 0) {
     // padding occupies the leading indices: zero columns 0..npad-1 of the staged triangle (only the first m rows
@@ -230,7 +273,7 @@ __device__ __forceinline__ void ws_fill_set(const UParams& q, const WsPoint<Band
   if (r < P) buf[tri_col(r, P)] = dg;
 }
 
-template <int P, int D>
+template <int P, int D, bool GENERAL>
 __global__ void __launch_bounds__(kWsThreads, 1)
 u_band_ws_kernel(const UParams q) {
   constexpr int G = 8;
@@ -391,7 +434,7 @@ u_band_ws_kernel(const UParams q) {
         const WsPoint<LY::DD> cur = pt;
         pt = ws_gather_set<P, D>(q, sidx_of(j + 1), raw, scratch, lane, d);
         raw = ws_load_raw(q, sidx_of(j + 2), lane, p);
-        ws_fill_set<P, D>(q, cur, buf, buf + LY::kBuf, wtab, &pdump[pw][lane], etab, lane, d, p);
+        ws_fill_set<P, D, GENERAL>(q, cur, buf, buf + LY::kBuf, wtab, &pdump[pw][lane], etab, lane, d, p);
         __syncwarp();
         if (lane == 0) ws_signal(&full_cnt[c][slot][sub], fill);
       }

@@ -70,7 +70,7 @@ void run_sets(int grid, const gpv::UParams& q) {
 }
 template <int P, int D>
 void run_ws(int grid, const gpv::UParams& q) {
-  run_grid(gpv::u_band_ws_kernel<P, D>, grid, gpv::kWsThreads, gpv::WsLayout<P, D>::kBytesPerBlock, q);
+  run_grid(gpv::u_band_ws_kernel<P, D, false>, grid, gpv::kWsThreads, gpv::WsLayout<P, D>::kBytesPerBlock, q);
 }
 template <int G, int P, int D>
 void run_band_general(int grid, const gpv::UParams& q) {
@@ -137,7 +137,7 @@ extern "C" int emu_u_sets(int family, int G, int P, int D, int grid, int64_t nse
 // General-nu Matern (Matern.cpp:72-83) through the table path: the coefficient table is built by the library's
 // own build_cov_table_kernel (one 32-thread block per interval, emulated like the set kernels) with the host
 // set-up of cov_setup.h, then u_band_kernel<G, P, D, general> runs on it.  w_max: squared bounding-box diagonal.
-extern "C" int emu_u_band_general(int G, int P, int D, int grid, int64_t nsets, int p, int d, const double* locs,
+extern "C" int emu_u_band_general(int family, int G, int P, int D, int grid, int64_t nsets, int p, int d, const double* locs,
                                   const int32_t* nn, const uint64_t* cond, const double* nuggets, double* out,
                                   unsigned long long* nfail, long long* first_fail, double sig2, double range,
                                   double nu, double w_max) {
@@ -155,8 +155,10 @@ extern "C" int emu_u_band_general(int G, int P, int D, int grid, int64_t nsets, 
   const double inv_range = q.inv_range;
   double* cp = coef.data();
   run_grid_fn([&]() { gpv::build_cov_table_kernel(t, inv_range, cp); }, t.nint, 32, 0);
-  if (G == 8 && P == 31 && D == 2) run_band_general<8, 31, 2>(grid, q);
-  else if (G == 16 && P == 41 && D == 3) run_band_general<16, 41, 3>(grid, q);
+  if (family == 2 && P == 31 && D == 2)
+    run_grid(gpv::u_band_ws_kernel<31, 2, true>, grid, gpv::kWsThreads, gpv::WsLayout<31, 2>::kBytesPerBlock, q);
+  else if (family == 1 && G == 8 && P == 31 && D == 2) run_band_general<8, 31, 2>(grid, q);
+  else if (family == 1 && G == 16 && P == 41 && D == 3) run_band_general<16, 41, 3>(grid, q);
   else return 1;
   return 0;
 }

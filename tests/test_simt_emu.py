@@ -308,14 +308,15 @@ def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp, 
         assert np.allclose(partials.reshape(-1, 4).sum(axis=0), pb.reshape(-1, 4).sum(axis=0), rtol=1e-13, atol=0)
 
 
-@pytest.mark.parametrize("G,P,m,d,nu", [(8, 31, 30, 2, 0.8), (8, 31, 30, 2, 1.3), (16, 41, 40, 3, 2.2)])
-def test_general_nu_table_path_on_the_host(emu_dir, G, P, m, d, nu):
+@pytest.mark.parametrize("family,G,P,m,d,nu", [(1, 8, 31, 30, 2, 0.8), (1, 8, 31, 30, 2, 1.3), (1, 16, 41, 40, 3, 2.2),
+                                               (2, 8, 31, 30, 2, 0.8), (2, 8, 31, 27, 2, 1.3)])
+def test_general_nu_table_path_on_the_host(emu_dir, family, G, P, m, d, nu):
     """General-nu Matern (Matern.cpp:72-83): the coefficient table built by the library's own
     build_cov_table_kernel and read by u_band_kernel<general>, both emulated, against the oracle's
     std::cyl_bessel_k restatement.  Includes duplicated locations (distance 0 -> sigma^2, :76-77) through the
-    kernel's slow path."""
+    kernel's slow path.  family 2: the warp-specialised experiment's general instantiation."""
     L = _build(emu_dir)
-    L.emu_u_band_general.argtypes = [C.c_int] * 4 + [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_double] * 4
+    L.emu_u_band_general.argtypes = [C.c_int] * 5 + [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_double] * 4
     L.emu_u_band_general.restype = C.c_int
     n = 80
     locs, revNN, rcf = _problem(n, m, d, seed=int(nu * 10) + P)
@@ -333,7 +334,7 @@ def test_general_nu_table_path_on_the_host(emu_dir, G, P, m, d, nu):
     first = np.full(1, np.iinfo(np.int64).max, dtype=np.int64)
     lr = np.ascontiguousarray(locs)
     w_max = float(((locs.max(axis=0) - locs.min(axis=0)) ** 2).sum())
-    rc = L.emu_u_band_general(G, P, d, 2, n, p, d, lr.ctypes.data, nn.ctypes.data, cond.ctypes.data, nug.ctypes.data,
+    rc = L.emu_u_band_general(family, G, P, d, 2, n, p, d, lr.ctypes.data, nn.ctypes.data, cond.ctypes.data, nug.ctypes.data,
                               out.ctypes.data, nfail.ctypes.data, first.ctypes.data, cp[0], cp[1], cp[2], w_max)
     assert rc == 0 and int(nfail[0]) == 0 and ref["nfail"] == 0
     got = out.reshape(n, p)
