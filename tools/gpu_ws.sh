@@ -15,5 +15,6 @@ run default "" ""
 run ws "" ws
 [ -f gpvecchia_b200/variants/lib_wsfin.so ] && run wsfin $PWD/gpvecchia_b200/variants/lib_wsfin.so ws
 # parity on the GPU: bit-identical to the default kernel (opt-in test file)
+unset GPV_LIB_PATH GPV_KERNEL_FAMILY
 GPV_TEST_EXPERIMENTS=1 timeout 300 python -u -m pytest tests/test_experiments_gpu.py -m gpu -x -q -p no:cacheprovider > gpurun_out/ws_pytest.log 2>&1
 echo "rc=$?" >> gpurun_out/ws_pytest.log; tail -5 gpurun_out/ws_pytest.log
