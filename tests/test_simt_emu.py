@@ -341,3 +341,19 @@ def test_general_nu_table_path_on_the_host(emu_dir, family, G, P, m, d, nu):
     Lr = ref["Lentries"]
     assert np.array_equal(got == 0, Lr == 0)
     assert (np.abs(got - Lr) / np.abs(Lr).max(axis=1, keepdims=True)).max() < 1e-10
+
+
+@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
+def test_warp_specialised_edge_sizes_on_the_host(emu_dir, defs):
+    """Fewer sets than one pass, one set, sizes around the 16-set pass, more blocks than work: the slot hand-over
+    must terminate and the values must match the oracle."""
+    L = _build(emu_dir, defs)
+    for n in (1, 3, 17, 33, 65):
+        locs, revNN, rcf = _problem(max(n, 2), 30, 2, seed=n)
+        locs, revNN, rcf = locs[:n], revNN[:n], rcf[:n]
+        nug = np.full(n, 0.1)
+        ref = _oracle(locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5])["Lentries"]
+        for grid in (1, 3):
+            got, _, nfail, _, _ = _run(L, 8, 31, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5], grid=grid, family=2)
+            got = got.reshape(n, 31)
+            assert nfail == 0 and (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-10, (n, grid)
