@@ -180,6 +180,37 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_cpus(cuda_index):
+    """N > 1 only: run this rank on the CPUs NVML reports as local to its GPU before any pinned host buffer is
+    allocated, so that the ranks' 264 MB device-to-host copies land in the memory of the socket their GPU hangs
+    on instead of all in one (profiles/r01_bench_n8.json: the end-to-end value fell from 3.6e8 at N = 4 to
+    2.2e8 at N = 8).  GPV_BENCH_NUMA=0 turns it off.  Returns a description for `config`."""
+    if os.environ.get("GPV_BENCH_NUMA", "1") != "1":
+        return "off (GPV_BENCH_NUMA=0)"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(cuda_index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            hdl = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            bind_to_gpu_cpus.unbound = allowed      # restored before the CPU baseline, which uses every host core
+            os.sched_setaffinity(0, cpus)
+            return f"rank runs on the {len(cpus)} CPUs local to its GPU (of {len(allowed)})"
+        return "one affinity domain: nothing to bind"
+    except Exception as e:     # no NVML, no permission: measure unbound
+        return f"unavailable ({type(e).__name__})"
+
+
 def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None,
                        covType="matern"):
     """Times the restated reference (oracle/: OpenMP schedule(static) + LAPACK dpotrf/dtrtrs) on a
@@ -308,6 +339,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the gpvecchia_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        config["host_binding"] = bind_to_gpu_cpus(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -513,6 +545,8 @@ def main():
             pass
 
     cpu = None
+    if getattr(bind_to_gpu_cpus, "unbound", None):
+        os.sched_setaffinity(0, bind_to_gpu_cpus.unbound)
     if rank == 0 and not args.no_cpu_baseline:
         full = (revNN != 0).sum(axis=1) >= 2          # time the full sets only (the unit of `value`)
         rate, cores, sample = cpu_reference_rate(locs, revNN[full], revCond[full], rb, nuggets, covparms, covType=covType)
