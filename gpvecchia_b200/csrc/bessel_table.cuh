@@ -238,6 +238,22 @@ __device__ __forceinline__ double cov_general_fast(double r2, int idx, const Cov
   for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
   return acc;
 }
+// The same polynomial with the coefficients read from the shared-memory window of the table (u_band.cuh):
+// `cf` points at interval j of a coefficient-major array with GW intervals per row.  A warp's lanes sit on a
+// dozen neighbouring intervals, i.e. on different banks: about one wavefront per coefficient, where the
+// global-memory gather costs 2.4 (profiles/r02_u_band_general_*).
+template <int GW>
+__device__ __forceinline__ double cov_general_fast_shared(double r2, const double* __restrict__ cf) {
+  const int hi = __double2hiint(r2), lo = __double2loint(r2);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
+  const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
+  const double v = m - mc;
+  double acc = cf[kTabDeg * GW];
+#pragma unroll
+  for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, cf[k * GW]);
+  return acc;
+}
 // Slow path (per lane correct for anything): zero distance, far pairs (exp split), arguments outside
 // the table, NaN.
 static __device__ __noinline__ double cov_general_slow(double r2, const UParams& q, const double* __restrict__ etab) {

@@ -81,20 +81,17 @@ static void register_all() {
   register_kernels_B8_31(g_entries, &g_nentries);
   register_kernels_B8_32(g_entries, &g_nentries);
   register_kernels_B16_41(g_entries, &g_nentries);
-  register_kernels_WS(g_entries, &g_nentries);
 }
 const KernelEntry* select_kernel(int p, int d, bool general) {
   std::call_once(g_reg_once, register_all);
   const int want_d = (d == 2 || d == 3) ? d : 0;
   const char* fam = std::getenv("GPV_KERNEL_FAMILY");
   const bool no_band = fam && std::strcmp(fam, "fold") == 0;
-  const bool want_ws = fam && std::strcmp(fam, "ws") == 0;     // development knob: the warp-specialised experiment
   const KernelEntry* best = nullptr;
   for (int i = 0; i < g_nentries; ++i) {
     const KernelEntry& e = g_entries[i];
     if (e.D != want_d || e.P < p || e.general != general) continue;
     if (e.family == 1 && no_band) continue;
-    if (e.family == 2 && !want_ws) continue;
     if (!best || e.P < best->P || (e.P == best->P && e.family > best->family)) best = &e;
   }
   return best;

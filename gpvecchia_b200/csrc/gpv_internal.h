@@ -10,8 +10,7 @@ namespace gpv {
 struct KernelEntry {
   int G, P, D;                                 // D = 0: runtime d <= GPV_MAX_D
   bool general;                                // general-nu table kernel vs closed forms
-  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: band-folded, three or four rows per lane (u_band.cuh),
-                                               // 2: warp-specialised experiment (u_band_ws.cuh; only with GPV_KERNEL_FAMILY=ws)
+  int family;                                  // 0: two rows per lane (u_kernels.cuh), 1: band-folded, three or four rows per lane (u_band.cuh)
   const char* name;
   void (*kernel)(const UParams);
   int smem_bytes;
@@ -40,6 +39,5 @@ void register_kernels_B8_26(KernelEntry* out, int* n);
 void register_kernels_B8_31(KernelEntry* out, int* n);
 void register_kernels_B8_32(KernelEntry* out, int* n);
 void register_kernels_B16_41(KernelEntry* out, int* n);
-void register_kernels_WS(KernelEntry* out, int* n);
 
 }  // namespace gpv

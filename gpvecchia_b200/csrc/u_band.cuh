@@ -28,13 +28,6 @@ namespace gpv {
 #define GPV_BAND_MINB3 3
 #endif
 constexpr int kBandPairUnroll = GPV_BAND_PAIR_UNROLL;   // pair-stage iterations per loop trip
-// GPV_BAND_EARLY_RCP = 1 (experiment, not measured yet: DESIGN.md 9): the owner of row k+1 inverts its pivot
-// as soon as step k has updated it and publishes 1/d_{k+1} in the diagonal slot, so a step starts with
-// loads and a multiply instead of load -> MUFU.RCP64H -> 3 DFMA.  Same values as the default path.
-#ifndef GPV_BAND_EARLY_RCP
-#define GPV_BAND_EARLY_RCP 0
-#endif
-
 template <int G, int P, int D>
 struct BandLayout {
   static constexpr int NB = (P + G - 1) / G;               // bands: 3 or 4
@@ -53,15 +46,24 @@ struct BandLayout {
   static constexpr int kStage = kX + kNug + kZ + kI + kRawI + kMeta;
   static constexpr int kOffNug = kX, kOffZ = kX + kNug, kOffIds = kX + kNug + kZ,
                        kOffRaw = kX + kNug + kZ + kI, kOffMeta = kX + kNug + kZ + kI + kRawI;
+  // resident warps the register allocation is sized for: three bands of a G = 8 group fit 168 registers (3 blocks
+  // of 4 warps); everything else holds 255 registers, 8 warps per SM.  Those 8 warps are ONE block of 256 threads
+  // (round 2; two blocks of 128 before): the per-block tables exist once per SM, which is what makes room, inside
+  // the 227 KB of shared memory, for the conflict-free copy of the 2^(j/64) table (8 KB) and for the window of the
+  // general-nu coefficient table (10 KB) next to the 32 sets in flight.
+  static constexpr int kMinBlocks = (G == 8 && NB == 3) ? GPV_BAND_MINB3 : 1;
+  static constexpr int kWPB = (kMinBlocks == 1) ? 8 : 4;   // warps per block
+  static constexpr int kThreads = 32 * kWPB;
+  static constexpr bool kWideTables = (kMinBlocks == 1);   // replicated exp table / shared general-nu window
+  static constexpr int kExpStride = kWideTables ? 16 : 1;
+  static constexpr int kGenWin = kWideTables ? 64 : 0;      // intervals of the general-nu table kept in shared memory
   static constexpr int kSetsPerWarp = 32 / G;
   static constexpr int kRaw = kBuf + 2 * kStage;
   // every set starts on a 128-byte line plus a skew of {0, 64, 32, 96} bytes: the row segments of the
   // sets of a half-warp tile one line, and the broadcast words of a warp instruction fall into
   // different banks
   static constexpr int kDoubles = ((kRaw + 15) / 16) * 16 + 16;
-  static constexpr int kBytesPerBlock = kDoubles * 8 * kSetsPerWarp * kWarpsPerBlock;
-  // resident blocks the register allocation is sized for: three bands of a G = 8 group fit 168 registers
-  static constexpr int kMinBlocks = (G == 8 && NB == 3) ? GPV_BAND_MINB3 : 2;
+  static constexpr int kBytesPerBlock = kDoubles * 8 * kSetsPerWarp * kWPB;
   static_assert(G == 8 || G == 16, "lane groups of 8 or 16");
   static_assert(P > 2 * G && P <= 4 * G, "band-folded kernel: 2G < P <= 4G");
   static_assert(G == 8 || NB == 3, "four bands of 16 lanes do not fit the register file");
@@ -109,9 +111,12 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
                                                      const double* __restrict__ xs,
                                                      const double (&x)[BandLayout<G, P, D>::NB][BandLayout<G, P, D>::DD],
                                                      int gl, const uint4* __restrict__ stab,
-                                                     const double* __restrict__ etab, int d) {
+                                                     const double* __restrict__ etab,
+                                                     const double* __restrict__ gtab, int d) {
   using LY = BandLayout<G, P, D>;
   constexpr int NB = LY::NB;
+  constexpr int ES = (KIND == COV_GENERAL) ? 1 : LY::kExpStride;
+  constexpr int GW = (KIND == COV_GENERAL) ? LY::kGenWin : 0;
   const uint4* stab_lane = stab + gl;
   char* Asb = reinterpret_cast<char*>(As);
   const double guard = (KIND == COV_GENERAL) ? 0.0 : kMathC[7];
@@ -125,18 +130,26 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
     for (int b = 0; b < NB; ++b) r2[b] = pair_r2<D>(xs, LY::PX, x[b], jp[b], d, guard);
     if constexpr (KIND == COV_GENERAL) {
       int idx[NB];
-      bool sp = false;
+      bool sp = false, outside = false;
 #pragma unroll
       for (int b = 0; b < NB; ++b) sp |= cov_general_special(r2[b], q.tab, &idx[b]);
+      if constexpr (GW > 0) {
+        const int win0 = q.tab.nint - GW;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { idx[b] -= win0; outside |= (unsigned)idx[b] >= (unsigned)GW; }
+      }
       if (__any_sync(0xffffffffu, sp)) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) v[b] = cov_general_slow(r2[b], q, etab);
+      } else if (GW > 0 && !__any_sync(0xffffffffu, outside)) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast_shared<(GW > 0 ? GW : 1)>(r2[b], gtab + idx[b]);
       } else {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast(r2[b], idx[b], q.tab);
+        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast(r2[b], idx[b] + (GW > 0 ? q.tab.nint - GW : 0), q.tab);
       }
     } else {
-      cov_eval_n<KIND, NB>(r2, v, q, etab);
+      cov_eval_n<KIND, NB, C, ES>(r2, v, q, etab);
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b) *reinterpret_cast<double*>(Asb + so[b]) = v[b];
@@ -152,24 +165,25 @@ static __device__ __noinline__ void pair_stage_band_fn(CovConsts cc, double* __r
                                                        const double (&x)[BandLayout<G, P, D>::NB][BandLayout<G, P, D>::DD],
                                                        int gl, const uint4* __restrict__ stab,
                                                        const double* __restrict__ etab, int d) {
-  pair_stage_band_impl<KIND, G, P, D, CovConsts>(cc, As, xs, x, gl, stab, etab, d);
+  pair_stage_band_impl<KIND, G, P, D, CovConsts>(cc, As, xs, x, gl, stab, etab, nullptr, d);
 }
 template <int KIND, int G, int P, int D>
 __device__ __forceinline__ void pair_stage_band(const UParams& q, double* __restrict__ As,
                                                 const double* __restrict__ xs,
                                                 const double (&x)[BandLayout<G, P, D>::NB][BandLayout<G, P, D>::DD],
                                                 int gl, const uint4* __restrict__ stab,
-                                                const double* __restrict__ etab, int d) {
+                                                const double* __restrict__ etab,
+                                                const double* __restrict__ gtab, int d) {
   if constexpr (KIND != COV_GENERAL) {
     const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
     pair_stage_band_fn<KIND, G, P, D>(cc, As, xs, x, gl, stab, etab, d);
   } else {
-    pair_stage_band_impl<KIND, G, P, D, UParams>(q, As, xs, x, gl, stab, etab, d);
+    pair_stage_band_impl<KIND, G, P, D, UParams>(q, As, xs, x, gl, stab, etab, gtab, d);
   }
 }
 
 template <int G, int P, int D, bool GENERAL>
-__global__ void __launch_bounds__(kThreadsPerBlock, BandLayout<G, P, D>::kMinBlocks)
+__global__ void __launch_bounds__(BandLayout<G, P, D>::kThreads, BandLayout<G, P, D>::kMinBlocks)
 u_band_kernel(const UParams q) {
   using LY = BandLayout<G, P, D>;
   constexpr int NB = LY::NB, SETS = LY::kSetsPerWarp, PX = LY::PX;
@@ -195,9 +209,24 @@ u_band_kernel(const UParams q) {
   double* stage0 = buf + LY::kBuf;
 
   __shared__ uint4 stab[LY::kT * G];
-  __shared__ double etab[64];
+  // 2^(j/64): 64 doubles, or (closed forms of the 256-thread kernels) every entry 16 times so that lane l reads
+  // column l % 16 -- a half-warp's lookups then fall into 16 different bank pairs for any j
+  constexpr int ES = GENERAL ? 1 : LY::kExpStride;
+  __shared__ double etab_s[64 * ES];
   build_store_table_band<G, P, D>(stab);
-  if (threadIdx.x < 64) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+  for (int i = threadIdx.x; i < 64 * ES; i += blockDim.x) etab_s[i] = kExp2Tab[i / ES];
+  const double* etab = etab_s + (ES > 1 ? (lane & (ES - 1)) : 0);
+  // general nu: the top kGenWin intervals of the coefficient table (w from w_max 2^-32 up) in shared memory,
+  // coefficient-major like the global table; pairs outside it take the global-memory path
+  constexpr int GW = GENERAL ? LY::kGenWin : 0;
+  __shared__ double gtab[(GW > 0) ? (kTabDeg + 1) * GW : 1];
+  if constexpr (GW > 0) {
+    const int win0 = q.tab.nint - GW;
+    for (int i = threadIdx.x; i < (kTabDeg + 1) * GW; i += blockDim.x) {
+      const int k = i / GW, j = i % GW + win0;
+      gtab[i] = (j >= 0) ? q.tab.coef[tab_coef_index(k, j)] : 0.0;
+    }
+  }
   __syncthreads();
 
   // my rows; a row that does not exist (>= P, last band only) is clamped to P-1 and masked
@@ -211,8 +240,8 @@ u_band_kernel(const UParams q) {
   }
 
   double acc_quad = 0.0, acc_logd = 0.0, acc_qden = 0.0, acc_lden = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock * SETS;
-  const int64_t first = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * SETS;
+  const int64_t stride = (int64_t)gridDim.x * LY::kWPB * SETS;
+  const int64_t first = ((int64_t)blockIdx.x * LY::kWPB + warp) * SETS;
 
   // ---- input pipeline (cp.async; same two-stage scheme as u_sets_kernel) ---------------------------
   auto fetch_raw = [&](int64_t sidx, double* st) {
@@ -342,16 +371,18 @@ u_band_kernel(const UParams q) {
     }
 
     // ---- 3. covariance pairs -> shared staging (packed lower triangle) -------------------------------
+#if !GPV_HACK_NOPAIR   /* GPV_HACK_*: timing experiments only (wrong values), never set in the product build */
     if (GENERAL) {
-      pair_stage_band<COV_GENERAL, G, P, D>(q, buf, xs, x, gl, stab, etab, d);
+      pair_stage_band<COV_GENERAL, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d);
     } else {
       switch (q.cov) {
-        case COV_EXP: pair_stage_band<COV_EXP, G, P, D>(q, buf, xs, x, gl, stab, etab, d); break;
-        case COV_M15: pair_stage_band<COV_M15, G, P, D>(q, buf, xs, x, gl, stab, etab, d); break;
-        case COV_M25: pair_stage_band<COV_M25, G, P, D>(q, buf, xs, x, gl, stab, etab, d); break;
-        default: pair_stage_band<COV_ESQE, G, P, D>(q, buf, xs, x, gl, stab, etab, d); break;
+        case COV_EXP: pair_stage_band<COV_EXP, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d); break;
+        case COV_M15: pair_stage_band<COV_M15, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d); break;
+        case COV_M25: pair_stage_band<COV_M25, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d); break;
+        default: pair_stage_band<COV_ESQE, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d); break;
       }
     }
+#endif
     if (__any_sync(FULL, npad > 0)) {
       // padding occupies the leading indices: zero columns 0..npad-1 of the staged triangle
       __syncwarp();
@@ -376,7 +407,7 @@ u_band_kernel(const UParams q) {
 
   // ---- deterministic block reduction of the likelihood partial sums ---------------------------------
   if (q.partials != nullptr) {
-    __shared__ double red[kWarpsPerBlock][4];
+    __shared__ double red[LY::kWPB][4];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       acc_quad += __shfl_xor_sync(FULL, acc_quad, o);
@@ -388,7 +419,7 @@ u_band_kernel(const UParams q) {
     __syncthreads();
     if (threadIdx.x < 4) {
       double a = 0.0;
-      for (int w = 0; w < kWarpsPerBlock; ++w) a += red[w][threadIdx.x];
+      for (int w = 0; w < LY::kWPB; ++w) a += red[w][threadIdx.x];
       q.partials[4 * blockIdx.x + threadIdx.x] = a;
     }
   }

@@ -299,7 +299,10 @@ __device__ __forceinline__ void neg_sqrt_fast_n(const double (&w)[N], double (&o
 #pragma unroll
   for (int i = 0; i < N; ++i) out[i] = fma(a[i], ge[i], g[i]);
 }
-template <int N>
+// ES: stride of the 2^(j/64) table.  ES = 1: 64 doubles; ES = 16: every entry replicated 16 times and `etab`
+// already offset by lane % 16, so the 16 lanes of a half-warp read 16 different bank pairs whatever their j
+// (profiles/r02_*: the 64-entry table cost 4.8 wavefronts per lookup instead of 2).
+template <int N, int ES = 1>
 __device__ __forceinline__ void exp_negarg_fast_n(const double (&ns_in)[N], double (&out)[N],
                                                   const double* __restrict__ etab) {
   const double kShift = 6755399441055744.0;
@@ -313,7 +316,7 @@ __device__ __forceinline__ void exp_negarg_fast_n(const double (&ns_in)[N], doub
 #pragma unroll
   for (int i = 0; i < N; ++i) { kf[i] = t[i] - kShift; n[i] = __double2loint(t[i]); }
 #pragma unroll
-  for (int i = 0; i < N; ++i) { r[i] = fma(kf[i], kMathC[8], ns[i]); T[i] = etab[n[i] & 63]; }
+  for (int i = 0; i < N; ++i) { r[i] = fma(kf[i], kMathC[8], ns[i]); T[i] = etab[(n[i] & 63) * ES]; }
 #pragma unroll
   for (int i = 0; i < N; ++i) { r2[i] = r[i] * r[i]; qq[i] = fma(kMathC[3], r[i], kMathC[2]); }
 #pragma unroll
@@ -329,16 +332,17 @@ __device__ __forceinline__ void exp_negarg_fast_n(const double (&ns_in)[N], doub
     out[i] = __hiloint2double(__double2hiint(v[i]) + (n[i] >> 6) * 1048576, __double2loint(v[i]));
 }
 struct CovConsts { double c0, c1, c2, c3, c4; };   // what the closed forms read of UParams, by value
-template <int KIND, int N, class C>
+template <int KIND, int N, class C, int ES = 1>
 __device__ __forceinline__ void cov_eval_n(const double (&r2)[N], double (&v)[N], const C& q,
                                            const double* __restrict__ etab) {
   static_assert(KIND != COV_GENERAL, "closed forms only");
+  static_assert(GPV_PAIR_FAST || ES == 1, "the replicated exp table is read by exp_negarg_fast_n only");
   double sq[N], ns[N], e[N];
 #if GPV_PAIR_FAST
   neg_sqrt_fast_n<N>(r2, sq);
 #pragma unroll
   for (int i = 0; i < N; ++i) ns[i] = sq[i] * q.c1;
-  exp_negarg_fast_n<N>(ns, e, etab);
+  exp_negarg_fast_n<N, ES>(ns, e, etab);
 #else
   sqrt_pos_n<N>(r2, sq);
 #pragma unroll
@@ -363,7 +367,7 @@ __device__ __forceinline__ void cov_eval_n(const double (&r2)[N], double (&v)[N]
 #pragma unroll
     for (int i = 0; i < N; ++i) ns2[i] = r2[i] * (-q.c3);
 #if GPV_PAIR_FAST
-    exp_negarg_fast_n<N>(ns2, e2, etab);
+    exp_negarg_fast_n<N, ES>(ns2, e2, etab);
 #else
     exp_negarg_n<N>(ns2, e2, etab);
 #endif

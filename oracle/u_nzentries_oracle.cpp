@@ -6,14 +6,16 @@
 // bench.py's cpu_baseline / --impl reference legs use it, as the checker or as
 // the reported CPU baseline.
 //
-// PARITY STATUS: the reference itself cannot be compiled in this image (needs
-// R, Rcpp, RcppArmadillo, BH/Boost).  This restatement is pinned by
+// PARITY STATUS: pinned.  The reference's own sources (unmodified) are compiled by oracle/ref_build into
+// oracle/_ref/libgpvecchia_ref.so; this restatement reproduces its outputs BIT FOR BIT on the committed
+// fixture tests/golden/ref_compiled.npz and on fresh random inputs (tests/test_reference_pin.py).  It is kept
+// because it exposes what the compiled reference cannot: a row-range entry point (bench.py samples rows of a
+// 1e7-location problem), the textbook and __float128 modes, and no per-row heap traffic in the timed loop.
+// Further pins:
 //   * the reference's own known-answer test for the three Matern closed forms
 //     (tests/testthat/test-MaternFun.r:32-41) -> tests/test_oracle_golden.py
 //   * identities the reference states (vignette :128-139, test-createL.r:43-45)
 //   * mpmath.besselk golden vectors for the general-nu branch.
-// Cholesky/solve outputs and NN-path U values are "parity unpinned" by the
-// reference's own tests: no reference test asserts them.
 //
 // Third-party arithmetic the reference reaches through unvendored dependencies:
 //   * Armadillo chol(.,"upper") / solve(R, e)  (src/U_NZentries.cpp:61-62)

@@ -2,13 +2,12 @@
 // (gpvecchia_b200/csrc/u_band.cuh, unchanged source) on the CPU, one std::thread per CUDA thread, through
 // the stand-in builtins of cuda_runtime.h in this directory.  Built and driven by tests/test_simt_emu.py:
 //   g++ -std=c++17 -O1 -pthread -shared -fPIC -Itests/simt_emu -Igpvecchia_b200/csrc -Iinclude \
-//       [-DGPV_BAND_EARLY_RCP=1] tests/simt_emu/emu_harness.cpp -o libemu.so
+//       tests/simt_emu/emu_harness.cpp -o libemu.so
 #include "cuda_runtime.h"   // the stand-in (this directory comes first on the include path)
 #define GPV_DEFINE_TABLE_BUILDER
 #include "bessel_table.cuh"
 #include "cov_setup.h"
 #include "u_band.cuh"
-#include "u_band_ws.cuh"
 
 #include <cstdlib>
 #include <functional>
@@ -68,17 +67,13 @@ template <int G, int P, int D>
 void run_sets(int grid, const gpv::UParams& q) {
   run_grid(gpv::u_sets_kernel<G, P, D, false>, grid, gpv::kThreadsPerBlock, gpv::SetLayout<G, P, D>::kBytesPerBlock, q);
 }
-template <int P, int D>
-void run_ws(int grid, const gpv::UParams& q) {
-  run_grid(gpv::u_band_ws_kernel<P, D, false>, grid, gpv::kWsThreads, gpv::WsLayout<P, D>::kBytesPerBlock, q);
-}
 template <int G, int P, int D>
 void run_band_general(int grid, const gpv::UParams& q) {
-  run_grid(gpv::u_band_kernel<G, P, D, true>, grid, gpv::kThreadsPerBlock, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
+  run_grid(gpv::u_band_kernel<G, P, D, true>, grid, gpv::BandLayout<G, P, D>::kThreads, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
 }
 template <int G, int P, int D>
 void run_band(int grid, const gpv::UParams& q) {
-  run_grid(gpv::u_band_kernel<G, P, D, false>, grid, gpv::kThreadsPerBlock, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
+  run_grid(gpv::u_band_kernel<G, P, D, false>, grid, gpv::BandLayout<G, P, D>::kThreads, gpv::BandLayout<G, P, D>::kBytesPerBlock, q);
 }
 
 }  // namespace
@@ -91,12 +86,7 @@ void run_band(int grid, const gpv::UParams& q) {
 // family 1 = u_band_kernel (three or four rows per lane), family 0 = u_sets_kernel (two rows per lane; D = 0 is
 // the run-time-dimension instantiation).
 static int emu_launch(int family, int G, int P, int D, int grid, const gpv::UParams& q) {
-  if (family == 2) {            // warp-specialised experiment (u_band_ws.cuh)
-    if (P == 31 && D == 2) run_ws<31, 2>(grid, q);
-    else if (P == 32 && D == 3) run_ws<32, 3>(grid, q);
-    else if (P == 26 && D == 2) run_ws<26, 2>(grid, q);
-    else return 1;
-  } else if (family == 1) {
+  if (family == 1) {
     if (G == 8 && P == 31 && D == 2) run_band<8, 31, 2>(grid, q);
     else if (G == 8 && P == 21 && D == 3) run_band<8, 21, 3>(grid, q);
     else if (G == 16 && P == 41 && D == 3) run_band<16, 41, 3>(grid, q);
@@ -155,9 +145,7 @@ extern "C" int emu_u_band_general(int family, int G, int P, int D, int grid, int
   const double inv_range = q.inv_range;
   double* cp = coef.data();
   run_grid_fn([&]() { gpv::build_cov_table_kernel(t, inv_range, cp); }, t.nint, 32, 0);
-  if (family == 2 && P == 31 && D == 2)
-    run_grid(gpv::u_band_ws_kernel<31, 2, true>, grid, gpv::kWsThreads, gpv::WsLayout<31, 2>::kBytesPerBlock, q);
-  else if (family == 1 && G == 8 && P == 31 && D == 2) run_band_general<8, 31, 2>(grid, q);
+  if (family == 1 && G == 8 && P == 31 && D == 2) run_band_general<8, 31, 2>(grid, q);
   else if (family == 1 && G == 16 && P == 41 && D == 3) run_band_general<16, 41, 3>(grid, q);
   else return 1;
   return 0;

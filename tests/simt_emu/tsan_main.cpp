@@ -45,6 +45,5 @@ int main() {
   bad |= run(0, 16, 31, 2, 40);    // two-row kernel, two sets per warp
   bad |= run(0, 32, 51, 2, 20);    // two-row kernel, one set per warp
   bad |= run(1, 8, 21, 3, 60);     // three bands of eight lanes
-  bad |= run(2, 8, 31, 2, 100);    // warp-specialised experiment: slot hand-over between producer and consumer warps
   return bad;
 }

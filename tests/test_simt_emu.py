@@ -4,7 +4,6 @@ barriers for __syncthreads / __syncwarp, shuffles and ballots through a per-warp
 immediate copy, uninitialised shared memory filled with NaN) and its output is compared with the oracle:
 row-major and packed U values, zero fill, the fused likelihood partial sums, failure counting, missing
 entries, p < P padding, three instantiations (G = 8 with four bands, G = 8 and 16 with three bands, d = 2 / 3).
-The compile-time experiment GPV_BAND_EARLY_RCP must give bit-identical output to the default build.
 This is a check of index maps, compaction, elimination order and outputs; the parity tests proper are the
 `-m gpu` tests on a B200."""
 import ctypes as C
@@ -199,28 +198,7 @@ def test_band_kernel_missing_entries_packed_order_and_failures(emu_dir):
     assert np.all(gotp[~ok] == 0)                                    # a failed row is written as zeros (:64-66)
 
 
-def test_early_reciprocal_experiment_is_bit_identical(emu_dir):
-    base = _build(emu_dir)
-    early = _build(emu_dir, ("GPV_BAND_EARLY_RCP=1",))
-    for G, P, m, d in ((8, 31, 30, 2), (8, 21, 20, 3), (16, 41, 40, 3)):
-        n = 70
-        locs, revNN, rcf = _problem(n, m, d, seed=P, p_drop=0.1)
-        nug = np.random.default_rng(3).uniform(0.05, 0.15, n)
-        z = np.random.default_rng(4).standard_normal(n)
-        a, pa, fa, _, _ = _run(base, G, P, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5], z=z)
-        b, pb, fb, _, _ = _run(early, G, P, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5], z=z)
-        assert fa == fb == 0
-        assert np.array_equal(a, b) and np.array_equal(pa, pb)
-    # and with failing rows: same rows fail, same outputs
-    locs, revNN, rcf = _problem(60, 30, 2, seed=5, layout="z")
-    locs[3, 1] = np.nan
-    nug = np.full(60, 0.1)
-    a, _, fa, ia, _ = _run(base, 8, 31, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5])
-    b, _, fb, ib, _ = _run(early, 8, 31, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5])
-    assert fa == fb and ia == ib and np.array_equal(a, b, equal_nan=True)
-
-
-@pytest.mark.parametrize("defs", [(), ("GPV_BAND_EARLY_RCP=1",), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
+@pytest.mark.parametrize("defs", [()])
 def test_shared_memory_protocol_is_race_free_under_thread_sanitizer(tmp_path, defs):
     """One host thread per CUDA thread, barriers only where the kernel synchronises: an exchange through shared
     memory that no __syncwarp / __syncthreads orders is a data race ThreadSanitizer reports (tests/simt_emu/
@@ -244,12 +222,11 @@ def test_shared_memory_protocol_is_race_free_under_thread_sanitizer(tmp_path, de
         assert "ThreadSanitizer: data race" in rb.stderr + rb.stdout
 
 
-@pytest.mark.parametrize("family,defs", [(1, ()), (2, ()), (2, ("GPV_WS_FINISH_IN_PRODUCERS=1",))])
+@pytest.mark.parametrize("family,defs", [(1, ())])
 def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir, family, defs):
     """Seeded sweep through the emulated band kernel: set sizes p = 17..31 on the P = 31 instantiation, holes
     anywhere, mixed latent / response conditioning, and nuggets that include Inf on response-conditioned
-    neighbours (Vecchia-Laplace's missing data, vecchia_laplace_NR.R:108: that neighbour decouples).  Run for the
-    default band kernel and for both builds of the warp-specialised experiment."""
+    neighbours (Vecchia-Laplace's missing data, vecchia_laplace_NR.R:108: that neighbour decouples)."""
     L = _build(emu_dir, defs)
     rng = np.random.default_rng(20240601)
     for trial in range(6):
@@ -278,43 +255,12 @@ def test_randomised_shapes_masks_and_nuggets_on_the_host(emu_dir, family, defs):
         assert np.all(got[failed] == 0)
 
 
-@pytest.mark.parametrize("P,m,d,covType,cp", [
-    (31, 30, 2, "matern", [1.3, 0.25, 1.5]),
-    (31, 26, 2, "esqe", [0.7, 0.3, 0.4, 0.2]),          # p = 27 < P = 31
-    (32, 31, 3, "matern", [1.0, 0.5, 2.5]),             # even P: the half iteration t = P/2
-    (26, 25, 2, "matern", [1.0, 0.3, 0.5]),
-])
-@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",), ("GPV_WS_FINISH_IN_PRODUCERS=1", "GPV_BAND_EARLY_RCP=1")])
-def test_warp_specialised_experiment_on_the_host(emu_dir, P, m, d, covType, cp, defs):
-    """u_band_ws.cuh (producer warps fill the staged triangle warp-per-set, consumer warps run the shared
-    factorisation text): values against the oracle, zero fill, fused sums, a ragged tail, slot reuse over
-    several passes; and for P = 31, d = 2 bit-identical to u_band_kernel (same arithmetic per pair).  Second
-    build: the producers also run the sweep and the outputs (GPV_WS_FINISH_IN_PRODUCERS)."""
-    L = _build(emu_dir, defs)
-    n = 150                                   # 2 blocks x 16 sets per pass: five passes per block, slots reused
-    locs, revNN, rcf = _problem(n, m, d, seed=P * 7 + m, p_drop=0.1 if P == 31 and m == 26 else 0.0)
-    nug = np.random.default_rng(1).uniform(0.05, 0.15, n)
-    z = np.random.default_rng(2).standard_normal(n)
-    ref = _oracle(locs, revNN, rcf, nug, covType, cp)
-    got, partials, nfail, _, n0 = _run(L, 8, P, locs, revNN, rcf, nug, covType, cp, z=z, family=2)
-    got = got.reshape(n, m + 1)
-    Lr = ref["Lentries"]
-    assert nfail == 0 and not np.isnan(got).any()
-    assert np.array_equal(got == 0, Lr == 0)
-    assert (np.abs(got - Lr) / np.abs(Lr).max(axis=1, keepdims=True)).max() < 1e-10
-    if P == 31 and d == 2:
-        base, pb, _, _, _ = _run(L, 8, 31, locs, revNN, rcf, nug, covType, cp, z=z, family=1)
-        assert np.array_equal(base.reshape(n, m + 1), got)
-        assert np.allclose(partials.reshape(-1, 4).sum(axis=0), pb.reshape(-1, 4).sum(axis=0), rtol=1e-13, atol=0)
-
-
-@pytest.mark.parametrize("family,G,P,m,d,nu", [(1, 8, 31, 30, 2, 0.8), (1, 8, 31, 30, 2, 1.3), (1, 16, 41, 40, 3, 2.2),
-                                               (2, 8, 31, 30, 2, 0.8), (2, 8, 31, 27, 2, 1.3)])
+@pytest.mark.parametrize("family,G,P,m,d,nu", [(1, 8, 31, 30, 2, 0.8), (1, 8, 31, 30, 2, 1.3), (1, 16, 41, 40, 3, 2.2)])
 def test_general_nu_table_path_on_the_host(emu_dir, family, G, P, m, d, nu):
     """General-nu Matern (Matern.cpp:72-83): the coefficient table built by the library's own
     build_cov_table_kernel and read by u_band_kernel<general>, both emulated, against the oracle's
     std::cyl_bessel_k restatement.  Includes duplicated locations (distance 0 -> sigma^2, :76-77) through the
-    kernel's slow path.  family 2: the warp-specialised experiment's general instantiation."""
+    kernel's slow path."""
     L = _build(emu_dir)
     L.emu_u_band_general.argtypes = [C.c_int] * 5 + [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_double] * 4
     L.emu_u_band_general.restype = C.c_int
@@ -341,19 +287,3 @@ def test_general_nu_table_path_on_the_host(emu_dir, family, G, P, m, d, nu):
     Lr = ref["Lentries"]
     assert np.array_equal(got == 0, Lr == 0)
     assert (np.abs(got - Lr) / np.abs(Lr).max(axis=1, keepdims=True)).max() < 1e-10
-
-
-@pytest.mark.parametrize("defs", [(), ("GPV_WS_FINISH_IN_PRODUCERS=1",)])
-def test_warp_specialised_edge_sizes_on_the_host(emu_dir, defs):
-    """Fewer sets than one pass, one set, sizes around the 16-set pass, more blocks than work: the slot hand-over
-    must terminate and the values must match the oracle."""
-    L = _build(emu_dir, defs)
-    for n in (1, 3, 17, 33, 65):
-        locs, revNN, rcf = _problem(max(n, 2), 30, 2, seed=n)
-        locs, revNN, rcf = locs[:n], revNN[:n], rcf[:n]
-        nug = np.full(n, 0.1)
-        ref = _oracle(locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5])["Lentries"]
-        for grid in (1, 3):
-            got, _, nfail, _, _ = _run(L, 8, 31, locs, revNN, rcf, nug, "matern", [1.0, 0.3, 1.5], grid=grid, family=2)
-            got = got.reshape(n, 31)
-            assert nfail == 0 and (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-10, (n, grid)
