@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- conditioning sets/sec of createU (U_NZentries) on B200, per the round contract.
+"""bench.py -- conditioning sets/sec of createU (U_NZentries) and loglik evals/sec on B200, per the round contract.
 
   python bench.py --gpus N --steps K --warmup W            own arm (CUDA path through the C ABI)
-  python bench.py --impl reference --gpus N ...            CPU arm: the restated reference
-                                                           (oracle/, OpenMP + LAPACK) on host cores
+  python bench.py --impl reference --gpus N ...            CPU arm: the reference's own sources compiled here
+                                                           (oracle/_ref; the restatement if that is missing)
 
-Workload (BASELINE.json configs[1]): n = 1e6 uniform 2-D locations per GPU (weak scaling: n =
-N * 1e6, rows sharded by contiguous range, every rank holds all locations), m = 30, Matern
-nu = 1.5 closed form, standard Vecchia ('z') conditioning, per-location nuggets.  One step = one
-U_NZentries pass over the rank's rows.  `value` times the device-resident call (gpv_u_dev);
-`e2e` times the reference-facing call with host buffers (gpv_u_values_packed: nuggets H2D,
-packed U values D2H) -- the call createU() makes.
+Primary workload (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE.json configs[1] -- n = 1e6 uniform 2-D
+locations per GPU (weak scaling: n = N * 1e6, rows sharded by contiguous equal ranges, every rank holds all
+locations), m = 30, Matern nu = 1.5 closed form, standard Vecchia ('z') conditioning, per-location nuggets.  One
+step = one U_NZentries pass over the rank's rows.  `value` times the device-resident call (gpv_u_dev); `e2e` times
+the reference-facing call with host buffers (gpv_u_values_packed: nuggets H2D, packed U values D2H) -- the call
+createU() makes.
+
+North-star workload (`roofline.cfg3`, `e2e.cfg3`): BASELINE.json configs[2] -- n = 1e7 total (STRONG scaling),
+m = 30, general-nu Matern (nu = 0.8, the Bessel branch), sharded over the N ranks; createU sets/s, the fused
+likelihood (evals/s, one all-reduce of the partial sums), roofline fraction and, inside the run, parity: every rank
+compares sampled rows of its shard with the oracle, and the all-reduced log-likelihood is compared with the value
+a single GPU gives (tests/golden/bench_loglik.json).
 """
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import subprocess
@@ -27,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SIG2 = 1.0
+GOLD_LL = os.path.join(ROOT, "tests", "golden", "bench_loglik.json")
 
 
 def flops_per_set(p, d, cov):
@@ -122,6 +130,39 @@ WORKLOADS = {
 }
 
 
+def load_synth():
+    """The pure numpy / scipy input generators, loaded BY PATH: importing the package would map the product's
+    .so, which the reference arm must not do."""
+    spec = importlib.util.spec_from_file_location("gpv_synth", os.path.join(ROOT, "gpvecchia_b200", "_synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_text(name, wl, n_total):
+    cov_desc = f"Matern nu={wl['nu']}" if wl["covType"] == "matern" else "esqe"
+    return (f"{name}: createU/U_NZentries, n={n_total} uniform {wl['d']}-D locs"
+            f"{' (' + str(wl['n']) + '/GPU)' if wl['scaling'] == 'weak' else ''}"
+            f"{' + ' + str(wl['n_pred']) + ' prediction locs' if wl['n_pred'] else ''}, m={wl['m']}, {cov_desc}, "
+            f"'{wl['layout']}' conditioning")
+
+
+def build_config(name, wl, n_total, world, north):
+    """`config` of the JSON line: the same for both arms (the driver compares them)."""
+    p = wl["m"] + 1
+    per_row_mb = (p * 4 + p * 8) / 1e6
+    cfg = dict(workload=workload_text(name, wl, n_total), n=n_total, m=wl["m"], d=wl["d"], covmodel=wl["covType"],
+               nu=wl["nu"], cond_yz=wl["layout"],
+               sharding=(f"rows by contiguous equal ranges over {world} rank(s) (sum n0^3 balanced for layouts with "
+                         "trivial rows); locs and nuggets replicated, ids / conditioning masks / outputs sliced"),
+               l2=(f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank "
+                   + ("(larger than the 126 MB L2)" if per_row_mb * n_total / world > 126 else
+                      "(fits the 126 MB L2: this workload is launch-latency bound, not a bandwidth case)")))
+    if north is not None:
+        cfg["north_star_workload"] = workload_text("cfg3", north, north["n"]) + f", strong scaling over {world} rank(s)"
+    return cfg
+
+
 def make_inputs(wl, n_total, world, rank, device, use_gpu_nn=True):
     """Synthetic problem of the workload; returns a dict with the rank's rows of revNN/revCond and
     the replicated arrays.  n_total = number of observed locations."""
@@ -134,10 +175,9 @@ def make_inputs(wl, n_total, world, rank, device, use_gpu_nn=True):
     tau = H.make_nuggets(n_total, stream=2)
     z = H.make_data(n_total, stream=2)
     if wl["layout"] == "z":
-        # 'z' conditioning: neighbours on the response, self on the latent (vecchia_specify.R:189-190)
-        # equal expected kernel time per rank (late rows gather from more than the L2 holds); the closed
-        # forms feel it twice as much, relatively, as the slower general-nu kernel
-        cuts = shard.locality_cuts(n_total, world, d, penalty_scale=1.0 if wl["tag"] != "general" else 0.5)
+        # 'z' conditioning: neighbours on the response, self on the latent (vecchia_specify.R:189-190).  Plain equal
+        # row ranges: with the library's locality layer a late row costs what an early one does.
+        cuts = shard.uniform_cuts(n_total, world)
         rb, re_ = int(cuts[rank]), int(cuts[rank + 1])
         if use_gpu_nn:
             revNN = H.ordered_nn_gpu(locs_obs, m, rb, re_, device=device)
@@ -146,10 +186,10 @@ def make_inputs(wl, n_total, world, rank, device, use_gpu_nn=True):
         revCond = np.zeros(revNN.shape, dtype=np.int32)
         revCond[revNN == 0] = np.iinfo(np.int32).min
         revCond[:, -1] = 1
-        nfull_total = n_total - 1
         return dict(locs=locs_obs, revNN=revNN, revCond=revCond, obs=np.ones(n_total, dtype=np.int32),
                     nug_all=tau, nug_obs=tau, z=z, covparms=covparms, rb=rb, re=re_, N=n_total,
-                    skip_rows=0, nfull_total=nfull_total, nfull_rank=int((revNN != 0).sum(axis=1).__ge__(2).sum()))
+                    skip_rows=0, nfull_total=n_total - 1, nfull_rank=int(((revNN != 0).sum(axis=1) >= 2).sum()),
+                    obs_lo=rb, obs_hi=re_)
     # response-first zy layout, optionally with prediction locations (vecchia_specify.R:191-224)
     n_p = wl["n_pred"]
     if n_p > 0:
@@ -165,14 +205,16 @@ def make_inputs(wl, n_total, world, rank, device, use_gpu_nn=True):
     revCond = H.rev(Cond[rb:re_]).astype(np.int32)
     revCond[revCond < 0] = np.iinfo(np.int32).min
     nug_all = np.concatenate([tau, np.zeros(N - n_total)])      # createU.R:75-77 with ord = identity
+    ocuts = shard.uniform_cuts(n_total, world)    # the observations' Z entries: any disjoint split will do
     return dict(locs=locs2, revNN=revNN, revCond=revCond, obs=obs.astype(np.int32), nug_all=nug_all,
                 nug_obs=tau, z=z, covparms=covparms, rb=rb, re=re_, N=N, skip_rows=n_total,
-                nfull_total=int((n0 >= 2).sum()), nfull_rank=int((n0[rb:re_] >= 2).sum()))
+                nfull_total=int((n0 >= 2).sum()), nfull_rank=int((n0[rb:re_] >= 2).sum()),
+                obs_lo=int(ocuts[rank]), obs_hi=int(ocuts[rank + 1]))
 
 
 def host_threads():
     """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so
-    omp_get_max_threads() would understate the box; the oracle takes the team size as an argument
+    omp_get_max_threads() would understate the box; the CPU arms take the team size as an argument
     (num_threads(Ncores), like src/U_NZentries.cpp:37)."""
     try:
         return len(os.sched_getaffinity(0))
@@ -182,9 +224,8 @@ def host_threads():
 
 def bind_to_gpu_cpus(cuda_index):
     """N > 1 only: run this rank on the CPUs NVML reports as local to its GPU before any pinned host buffer is
-    allocated, so that the ranks' 264 MB device-to-host copies land in the memory of the socket their GPU hangs
-    on instead of all in one (profiles/r01_bench_n8.json: the end-to-end value fell from 3.6e8 at N = 4 to
-    2.2e8 at N = 8).  GPV_BENCH_NUMA=0 turns it off.  Returns a description for `config`."""
+    allocated, so that the ranks' device-to-host copies land in the memory of the socket their GPU hangs on.
+    GPV_BENCH_NUMA=0 turns it off.  Returns a description."""
     if os.environ.get("GPV_BENCH_NUMA", "1") != "1":
         return "off (GPV_BENCH_NUMA=0)"
     try:
@@ -211,31 +252,370 @@ def bind_to_gpu_cpus(cuda_index):
         return f"unavailable ({type(e).__name__})"
 
 
-def cpu_reference_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, target_s=12.0, threads=None,
-                       covType="matern"):
-    """Times the restated reference (oracle/: OpenMP schedule(static) + LAPACK dpotrf/dtrtrs) on a
-    bounded sample of the same workload's rows; returns (sets/s, threads, sample description)."""
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arms.  The compiled reference (oracle/_ref: the reference's own U_NZentries.cpp / Matern.cpp / Esqe.cpp /
+# dist.cpp, unmodified) processes every row of the problem it is given, so its sample is the FIRST k rows of the
+# workload -- a self-contained problem, because ordered-NN rows only name earlier rows -- with the workload's
+# covparms.  The restatement (oracle/) has a row-range entry point and is timed on the LAST rows as well.
+# ---------------------------------------------------------------------------------------------------------------
+def reference_prefix_problem(S, wl, n_total, k):
+    """First k rows (full conditioning sets from row m on) of the n_total-location workload, marshalled for the
+    compiled reference."""
+    from oracle import ref_native as RN
+    d, m = wl["d"], wl["m"]
+    rng_ = S.default_range(n_total, d)
+    covparms = np.array([SIG2, rng_, wl["nu"]]) if wl["covType"] == "matern" else np.array([1.0, rng_, 0.5, rng_])
+    locs = S.make_locs(n_total, d, stream=2)[:k]
+    tau = S.make_nuggets(n_total, stream=2)[:k]
+    NN = S.ordered_nn_kdtree(locs, m)
+    if wl["layout"] == "z":
+        revNN = S.rev(NN).astype(np.int32)
+        revCond = np.zeros(revNN.shape, dtype=np.int32)
+        revCond[revNN == 0] = np.iinfo(np.int32).min
+        revCond[:, -1] = 1
+        return RN.Problem(k, locs, revNN, revCond, tau, tau, wl["covType"], covparms), k - 1
+    locs2, NN2, Cond, obs = S.layout_zy(locs, m, k)          # zy: k dummy rows + k full rows
+    revCond = S.rev(Cond).astype(np.int32)
+    revCond[revCond < 0] = np.iinfo(np.int32).min
+    nug_all = np.concatenate([tau, np.zeros(k)])
+    return RN.Problem(k, locs2, S.rev(NN2).astype(np.int32), revCond, nug_all, tau, wl["covType"], covparms), k
+
+
+def time_reference(S, wl, n_total, threads, target_s, backends=("openblas", "textbook")):
+    """(sets/s, backend, k, passes, seconds) of the compiled reference on about target_s seconds of CPU work: a pilot
+    picks the faster of LAPACK (OpenBLAS from scipy) and the published unblocked chol / back substitution."""
+    from oracle import ref_native as RN
+    k0 = 4000
+    pr, nfull = reference_prefix_problem(S, wl, n_total, k0)
+    rates = {}
+    for b in backends:
+        RN.force_textbook(b == "textbook")
+        pr.run(threads)
+        t0 = time.perf_counter()
+        pr.run(threads)
+        rates[b] = nfull / (time.perf_counter() - t0)
+    best = max(rates, key=rates.get)
+    RN.force_textbook(best == "textbook")
+    k = int(min(200_000, max(k0, rates[best] * min(target_s, 4.0))))
+    pr, nfull = reference_prefix_problem(S, wl, n_total, k)
+    pr.run(threads)                                      # page-fault / thread-pool warm-up
+    passes = max(1, int(round(target_s / max(nfull / rates[best], 1e-3))))
+    per = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        pr.run(threads)
+        per.append(time.perf_counter() - t0)
+    RN.force_textbook(False)
+    # the median pass: a pass that shared the cores with something else does not set the number
+    return nfull / float(np.median(per)), best, k, passes, float(np.sum(per)), rates
+
+
+def port_rate(locs, revNN_rows, revCond_rows, row_begin, nuggets, covparms, covType, threads, target_s, mode=0):
+    """The restatement (oracle/, OpenMP schedule(static) + LAPACK, no per-row heap traffic) on the LAST rows of the
+    workload; (sets/s, description)."""
     import oracle as O
-    threads = threads or host_threads()
-    n_total = locs.shape[0]
     nr = revNN_rows.shape[0]
 
     def timed(nrows_s):
         pr = O.RowsProblem(locs, revNN_rows[nr - nrows_s:], revCond_rows[nr - nrows_s:], row_begin + nr - nrows_s,
                            nuggets, covType, covparms)
         t0 = time.perf_counter()
-        pr.run(threads)
+        pr.run(threads, mode=mode)
         return time.perf_counter() - t0
     pilot = min(20000, nr)
-    timed(min(2000, nr))                      # thread-pool / page-fault warm-up
+    timed(min(2000, nr))
     t_p = timed(pilot)
     nrows_s = int(min(nr, max(pilot, pilot / t_p * target_s)))
-    # about target_s seconds of CPU work in total: repeat the pass when the rank has too few rows
-    passes = int(min(10, max(1, round(target_s / max(nrows_s * t_p / pilot, 1e-3)))))
-    t_s = sum(timed(nrows_s) for _ in range(passes))
-    lo = row_begin + nr - nrows_s
-    return (nrows_s * passes / t_s, threads,
-            f"rows [{lo},{lo + nrows_s}) of the n={n_total} workload x {passes} passes, {t_s:.1f} s of CPU time")
+    t_s = timed(nrows_s)
+    return nrows_s / t_s, f"last {nrows_s} rows of the n={locs.shape[0]} workload, {t_s:.1f} s"
+
+
+def cpu_baseline_block(wl, n_total, pb, full_mask):
+    """`cpu_baseline` of the own arm (rank 0, N = 1): the compiled reference on all host cores (the headline CPU
+    number), on one core, a core-scaling table, and the restatement beside it."""
+    S = load_synth()
+    threads = host_threads()
+    out = {}
+    try:
+        from oracle import ref_native as RN
+        have_ref = RN.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        _, backend, _, _, _, _ = time_reference(S, wl, n_total, threads, target_s=1.0)
+        by = {}
+        for c in sorted({1, 8, 16, 32, threads}):
+            if c <= threads:
+                by[str(c)] = time_reference(S, wl, n_total, c, target_s=2.0, backends=(backend,))[0]
+        rate, backend, k, passes, dt, rates = time_reference(S, wl, n_total, threads, target_s=10.0)
+        out.update(value=rate, unit="sets/s", cores=threads, kind="reference",
+                   sample=(f"the reference's own U_NZentries.cpp (oracle/_ref) on the first {k} rows of the n={n_total} "
+                           f"workload (self-contained: ordered-NN rows only name earlier rows), same covparms, median of {passes} "
+                           f"passes ({dt:.1f} s in all); chol/solve backend {backend} (pilot: "
+                           + ", ".join(f"{b} {v:.3g}" for b, v in rates.items()) + " sets/s)"))
+        out["by_cores"] = by
+        out["one_core"] = by.get("1")
+    locs, revNN, revCond = pb["locs"], pb["revNN"][full_mask], pb["revCond"][full_mask]
+    pr, ps = port_rate(locs, revNN, revCond, pb["rb"], pb["nug_all"], pb["covparms"], wl["covType"], threads, 4.0)
+    p1, _ = port_rate(locs, revNN, revCond, pb["rb"], pb["nug_all"], pb["covparms"], wl["covType"], 1, 2.0)
+    pt, _ = port_rate(locs, revNN, revCond, pb["rb"], pb["nug_all"], pb["covparms"], wl["covType"], threads, 3.0, mode=1)
+    out["port"] = {"value": max(pr, pt), "lapack": pr, "textbook": pt, "one_core": p1, "cores": threads,
+                   "sample": ps, "what": "oracle/ restatement (same arithmetic as the reference, bit for bit; no "
+                                         "Armadillo-style temporaries), the faster of LAPACK and textbook chol"}
+    if not have_ref:
+        out.update(value=out["port"]["value"], unit="sets/s", cores=threads, kind="port", sample=ps)
+    return out
+
+
+def reference_arm(args, name, wl, n_total, world, north):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    S = load_synth()
+    threads = host_threads()
+    config = build_config(name, wl, n_total, world, north)
+    try:
+        from oracle import ref_native as RN
+        have_ref = RN.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        from oracle import ref_native as RN
+        rate0, backend, _, _, _, rates = time_reference(S, wl, n_total, threads, target_s=1.5)
+        RN.force_textbook(backend == "textbook")
+        k = int(min(200_000, max(4000, rate0 * 3.0)))        # ~3 s of CPU work per step
+        pr, nfull = reference_prefix_problem(S, wl, n_total, k)
+        run = lambda: pr.run(threads)                        # noqa: E731
+        kind = "reference"
+        sample = (f"{nfull} full sets per step: the reference's own U_NZentries.cpp (oracle/_ref) on the first {k} rows of "
+                  f"the n={n_total} workload (self-contained: ordered-NN rows only name earlier rows), same covparms, "
+                  f"{threads} OpenMP threads, chol/solve backend {backend}")
+    else:
+        import oracle as O
+        k = 60_000
+        locs = S.make_locs(n_total, wl["d"], stream=2)[:k]
+        tau = S.make_nuggets(n_total, stream=2)[:k]
+        revNN = S.rev(S.ordered_nn_kdtree(locs, wl["m"])).astype(np.int32)
+        revCond = np.zeros(revNN.shape, dtype=np.int32)
+        revCond[revNN == 0] = np.iinfo(np.int32).min
+        revCond[:, -1] = 1
+        rng_ = S.default_range(n_total, wl["d"])
+        cp = np.array([SIG2, rng_, wl["nu"]]) if wl["covType"] == "matern" else np.array([1.0, rng_, 0.5, rng_])
+        po = O.RowsProblem(locs, revNN, revCond, 0, tau, wl["covType"], cp)
+        run = lambda: po.run(threads)                        # noqa: E731
+        nfull, kind = k - 1, "port"
+        sample = f"{nfull} full sets per step: oracle/ restatement on the first {k} rows, {threads} OpenMP threads"
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = nfull * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": "sets/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank's GPU: device-resident steps, end-to-end steps, likelihood, parity sample."""
+
+    def __init__(self, name, wl, n_total, world, rank, local_rank, host_nn=False):
+        import torch
+        import gpvecchia_b200 as G
+        self.torch, self.G = torch, G
+        self.name, self.wl, self.n_total, self.world, self.rank, self.local_rank = name, wl, n_total, world, rank, local_rank
+        self.dev = torch.device("cuda", local_rank)
+        t0 = time.perf_counter()
+        self.pb = pb = make_inputs(wl, n_total, world, rank, local_rank, use_gpu_nn=not host_nn)
+        self.t_gen = time.perf_counter() - t0
+        self.p = wl["m"] + 1
+        self.nrows = pb["re"] - pb["rb"]
+        t0 = time.perf_counter()
+        self.h = G.UHandle(pb["locs"], pb["revNN"], pb["revCond"], obs=pb["obs"], row_begin=pb["rb"], row_end=pb["re"],
+                           device=local_rank)
+        self.t_create = time.perf_counter() - t0
+        self.d_nug = torch.from_numpy(pb["nug_all"]).to(self.dev)
+        self.d_out = torch.empty(self.nrows * self.p, dtype=torch.float64, device=self.dev)
+        self.d_z = torch.from_numpy(pb["z"]).to(self.dev)
+        self.d_ll = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        self.tstream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """W untimed steps, then exactly `steps` between two CUDA events on the launching stream, a barrier +
+        synchronize on both sides, MAX over ranks (ms)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        self.h.kernel_time_stats(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.allmax(e0.elapsed_time(e1))
+
+    def step_dev(self, covType=None, covparms=None):
+        pb = self.pb
+        self.h.u_dev(covType or self.wl["covType"], pb["covparms"] if covparms is None else covparms,
+                     self.d_nug.data_ptr(), self.d_out.data_ptr(), packed=False, stream=self.stream)
+
+    def step_ll(self):
+        from gpvecchia_b200 import shard
+        pb = self.pb
+        self.h.u_dev(self.wl["covType"], pb["covparms"], self.d_nug.data_ptr(), None, d_zord=self.d_z.data_ptr(),
+                     skip_rows=pb["skip_rows"], d_loglik=self.d_ll.data_ptr(), stream=self.stream)
+        if self.world > 1:
+            shard.allreduce_loglik(self.d_ll)          # a handful of doubles over NCCL: the path's only collective
+
+    def loglik_value(self):
+        """Whole log-likelihood of a pure-z layout from the all-reduced partial sums of the last step_ll()."""
+        pb = self.pb
+        parts = [float(v) for v in self.d_ll.cpu().tolist()]
+        z, tau = pb["z"], pb["nug_obs"]
+        qn = parts[0] + float(np.sum(z * z / tau))
+        ldn = parts[1] + float(np.sum(np.log(tau)))
+        out = dict(quadform_num=qn, logdet_num=ldn, quadform_denom=parts[3], logdet_denom=parts[4], nfail=parts[2])
+        if self.wl["layout"] == "z":
+            out["loglik"] = -0.5 * (ldn - parts[4] + qn - parts[3] + self.n_total * float(np.log(2 * np.pi)))
+        return out
+
+    def parity_sample(self, nsample=2000):
+        """Max row-scaled error of sampled rows of THIS rank's shard (device-resident output of the last step_dev)
+        against the oracle restatement on the same rows; MAX over ranks.  North_star bar: 1e-10."""
+        import oracle as O
+        pb = self.pb
+        full = np.nonzero((pb["revNN"] != 0).sum(axis=1) >= 2)[0]
+        rs = np.random.default_rng(1234 + self.rank)
+        rows = np.sort(rs.choice(full, size=min(nsample, full.size), replace=False))
+        self.torch.cuda.synchronize()
+        idx = self.torch.from_numpy(rows).to(self.dev)
+        got = self.d_out.view(self.nrows, self.p).index_select(0, idx).cpu().numpy()
+        pr = O.RowsProblem(pb["locs"], pb["revNN"][rows], pb["revCond"][rows], 0, pb["nug_all"], self.wl["covType"],
+                           pb["covparms"])
+        pr.run(host_threads())
+        ref = pr.Lentries()
+        err = float((np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max())
+        same_pattern = bool(np.array_equal(got == 0, ref == 0))
+        return self.allmax(err if same_pattern else 1.0), rows.size
+
+    def e2e(self, steps):
+        """The reference-facing call with HOST buffers: gpv_u_values_packed (createU's U_NZentries + packing).  Every
+        rank uploads the per-location nuggets and the nuggets of ITS slice of the observations, and downloads its
+        rows' packed U values and its slice of Zentries; wall clock around `steps` calls, barrier on both sides,
+        MAX over ranks.  Also times plain pinned D2H copies of the same size: the box's ceiling for this call."""
+        torch, pb, h = self.torch, self.pb, self.h
+        n_obs_slice = pb["obs_hi"] - pb["obs_lo"]
+        total = h.packed_len + 2 * n_obs_slice
+        host_out = torch.empty(total, dtype=torch.float64).pin_memory()
+        host_nug = torch.from_numpy(pb["nug_all"]).pin_memory()
+        host_tau = torch.from_numpy(np.ascontiguousarray(pb["nug_obs"][pb["obs_lo"]:pb["obs_hi"]])).pin_memory()
+        out_np, nug_np, tau_np = host_out.numpy(), host_nug.numpy(), host_tau.numpy()
+        self.e2e_bufs = (out_np, nug_np, tau_np)
+
+        def step():
+            h.values_packed(self.wl["covType"], pb["covparms"], nug_np, tau_np, zentries_tail=True, out=out_np)
+        for _ in range(2):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.barrier()
+        dt = self.allmax(time.perf_counter() - t0)
+        h2d = 8 * (pb["nug_all"].size + n_obs_slice)
+        d2h = 8 * total
+        # ceiling: the same number of bytes as plain pinned copies, all ranks at once
+        d_src = torch.empty(total, dtype=torch.float64, device=self.dev)
+        for _ in range(2):
+            host_out.copy_(d_src, non_blocking=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            host_out.copy_(d_src, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        self.barrier()
+        dt_copy = self.allmax(time.perf_counter() - t0)
+        del d_src
+        return dict(seconds_per_step=dt / steps, h2d=h2d, d2h=d2h, copy_seconds_per_step=dt_copy / steps)
+
+    def close(self):
+        self.h.close()
+        self.torch.cuda.set_stream(self.torch.cuda.default_stream(self.dev))
+
+
+def sum_over_ranks(v, runner):
+    t = runner.torch.tensor([float(v)], dtype=runner.torch.float64, device=runner.dev)
+    if runner.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def roofline_block(runner, k_ms, k_count, ms_step, peak_tf):
+    wl, pb = runner.wl, runner.pb
+    F = flops_per_set(runner.p, wl["d"], wl["tag"])
+    B = bytes_per_set(runner.p, wl["d"])
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    nfull_rank = pb["nfull_rank"]
+    achieved_tf = F * nfull_rank / (k_ms * 1e-3) / 1e12
+    kname = runner.h.last_kernel_name()
+    rl = {
+        "bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf,
+        "peak_source": "fp64 FMA peak from a DFMA micro-kernel in this run (gpv_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has HBM and bf16 only",
+        "flops_per_set": F, "sets_per_launch": nfull_rank, "kernel_ms": k_ms, "kernel_launches_timed": k_count,
+        "kernel_share_of_step": k_ms / ms_step,
+        "hbm": {"achieved": B * nfull_rank / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": B * nfull_rank / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_set": B, "peak_source": hbm_src},
+        "traffic": None,
+    }
+    # evidence from the committed ncu capture of THIS kernel (profiles/roofline_traffic.json, keyed by kernel name):
+    # DRAM bytes per launch, executed fp64 warp instructions per set
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("kernels", {}).get(kname)
+    except Exception:
+        pj = None
+    if pj:
+        if pj.get("sets_per_launch") == nfull_rank or abs(pj.get("sets_per_launch", 0) - nfull_rank) <= 1:
+            rl["traffic"] = pj.get("dram_bytes_per_launch")
+        ipset = pj.get("fp64_warp_inst_per_set")
+        if ipset:
+            # what the fp64 pipe physically did: executed fp64 warp instructions x 32 lanes x 2 flop / time / peak
+            rl["fp64_inst_frac"] = ipset * nfull_rank * 64.0 / (k_ms * 1e-3) / 1e12 / peak_tf
+            rl["max_algorithmic_frac_at_full_pipe"] = F / (ipset * 64.0)
+            rl["fp64_warp_inst_per_set"] = ipset
+        rl["ncu_source"] = pj.get("source")
+    return rl
 
 
 def main():
@@ -246,311 +626,187 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the workload's n (per GPU if weak, total if strong)")
+    ap.add_argument("--north-n", type=int, default=0, help="override n of the north-star (cfg3) section")
     ap.add_argument("--host-nn", action="store_true", help="build neighbour arrays with cKDTree on the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other covariances and the dgCMatrix@x call")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the cfg3 (n = 1e7, general nu) section")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = dict(WORKLOADS[args.workload])
+    name = args.workload
+    wl = dict(WORKLOADS[name])
     if args.n:
         wl["n"] = args.n
     n_total = wl["n"] * world if wl["scaling"] == "weak" else wl["n"]
-    m, d = wl["m"], wl["d"]
-    p = m + 1
-    cov_desc = f"Matern nu={wl['nu']}" if wl["covType"] == "matern" else "esqe"
-    workload = (f"{args.workload}: createU/U_NZentries, n={n_total} uniform {d}-D locs"
-                f"{' (' + str(wl['n']) + '/GPU on average)' if wl['scaling'] == 'weak' else ''}"
-                f"{' + ' + str(wl['n_pred']) + ' prediction locs' if wl['n_pred'] else ''}, m={m}, {cov_desc}, "
-                f"'{wl['layout']}' conditioning")
-    per_row_mb = (p * 4 + p * 8) / 1e6
-    config = dict(workload=workload, n=n_total, m=m, d=d, covmodel=wl["covType"], nu=wl["nu"], cond_yz=wl["layout"],
-                  sharding=(f"rows by contiguous range over {world} rank(s), cut for equal expected kernel time "
-                            "(late rows gather from more than the L2 holds: gpvecchia_b200/shard.py); locs and nuggets replicated"),
-                  l2=(f"touched per step: {per_row_mb * n_total / world:.0f} MB of ids + U values per rank "
-                      + ("(larger than the 126 MB L2)" if per_row_mb * n_total / world > 126 else
-                         "(fits the 126 MB L2: this workload is launch-latency bound, not a bandwidth case)")))
+    north = None
+    if name == "cfg2" and not args.no_north_star:
+        north = dict(WORKLOADS["cfg3"])
+        if args.north_n:
+            north["n"] = args.north_n
 
     if args.impl == "reference":
-        # ---- CPU arm: the restated reference (oracle/: OpenMP + LAPACK) on this box's host cores -----
-        if rank != 0:
-            return
-        import oracle as O
-        from gpvecchia_b200 import harness as H
-        try:
-            import gpvecchia_b200 as G
-            have_gpu = G.lib.gpv_device_count() > 0
-        except Exception:
-            have_gpu = False
-        use_gpu_nn = have_gpu and not args.host_nn
-        if wl["layout"] == "z":
-            n_s = min(n_total, 400_000)      # neighbour arrays for a bounded sample of the workload's rows
-            locs = H.make_locs(n_total, d, stream=2)
-            rb, re_ = n_total - n_s, n_total
-            if use_gpu_nn:
-                revNN = H.ordered_nn_gpu(locs, m, rb, re_, device=0)
-            else:
-                revNN = H.rev(H.ordered_nn_kdtree(locs, m, rb, re_)).astype(np.int32)
-            revCond = np.zeros(revNN.shape, dtype=np.int32)
-            revCond[revNN == 0] = np.iinfo(np.int32).min
-            revCond[:, -1] = 1
-            nuggets = H.make_nuggets(n_total, stream=2)
-            rng_ = H.default_range(n_total, d)
-            covparms = np.array([SIG2, rng_, wl["nu"]]) if wl["covType"] == "matern" else np.array([1.0, rng_, 0.5, rng_])
-        else:
-            pb = make_inputs(wl, n_total, 1, 0, 0, use_gpu_nn=use_gpu_nn)
-            full = (pb["revNN"] != 0).sum(axis=1) >= 2
-            locs, revNN, revCond, nuggets, covparms = pb["locs"], pb["revNN"][full], pb["revCond"][full], pb["nug_all"], pb["covparms"]
-            n_s = min(revNN.shape[0], 400_000)
-            revNN, revCond = revNN[-n_s:], revCond[-n_s:]
-            rb, re_ = pb["N"] - n_s, pb["N"]
-        threads = host_threads()
-        rate0, _, _ = cpu_reference_rate(locs, revNN, revCond, rb, nuggets, covparms, target_s=2.0, covType=wl["covType"])
-        rows_step = int(min(n_s, max(10000, rate0 * 3.0)))      # ~3 s of CPU work per step
-        pr = O.RowsProblem(locs, revNN[-rows_step:], revCond[-rows_step:], re_ - rows_step, nuggets, wl["covType"], covparms)
-        for _ in range(args.warmup):
-            pr.run(threads)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pr.run(threads)
-        dt = time.perf_counter() - t0
-        value = rows_step * args.steps / dt
-        sample = (f"{rows_step} full rows per step (rows [{re_ - rows_step},{re_}) of the n={n_total} workload), "
-                  f"{threads} OpenMP threads, LAPACK={'openblas' if O.has_lapack() else 'textbook'}")
-        print(json.dumps({
-            "impl": "reference", "metric": "conditioning sets/sec (createU)", "value": value, "unit": "sets/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config,
-            "cpu_baseline": {"value": value, "unit": "sets/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        if rank == 0:
+            reference_arm(args, name, wl, n_total, world, north)
         return
 
-    # ---- own arm --------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
     import gpvecchia_b200 as G
-    from gpvecchia_b200 import shard
 
     if G.lib.gpv_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the gpvecchia_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_binding = None
     if world > 1:
-        config["host_binding"] = bind_to_gpu_cpus(local_rank)
+        host_binding = bind_to_gpu_cpus(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    config = build_config(name, wl, n_total, world, north)
 
-    t_gen = time.perf_counter()
-    pb = make_inputs(wl, n_total, world, rank, local_rank, use_gpu_nn=not args.host_nn)
-    t_gen = time.perf_counter() - t_gen
-    locs, revNN, revCond, covparms, z = pb["locs"], pb["revNN"], pb["revCond"], pb["covparms"], pb["z"]
-    nuggets, nug_obs = pb["nug_all"], pb["nug_obs"]
-    rb, re_ = pb["rb"], pb["re"]
-    nrows = re_ - rb
-    n_sets = pb["nfull_total"]            # conditioning sets with n0 >= 2 over all ranks: the unit of `value`
-    # each rank hands over only its own rows of revNNarray / revCond (gpv_create_shard)
-    h = G.UHandle(locs, revNN, revCond, obs=pb["obs"], row_begin=rb, row_end=re_, device=local_rank)
-    covType = wl["covType"]
+    peak_tf = C.c_double(0)
+    G._lib.check(G.lib.gpv_measure_fp64_peak(local_rank, C.byref(peak_tf)))
+    peak_tf = peak_tf.value
 
-    d_nug = torch.from_numpy(nuggets).to(dev)
-    d_out = torch.empty(nrows * p, dtype=torch.float64, device=dev)
-    d_z = torch.from_numpy(z).to(dev)
-    d_ll = torch.zeros(8, dtype=torch.float64, device=dev)
-    # a dedicated (non-default) torch stream: its handle is what the C ABI launches on, and the
-    # torch events below are recorded on the same stream
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-
-    def step_dev():
-        h.u_dev(covType, covparms, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        h.kernel_time_stats(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
+    # ---- primary workload ---------------------------------------------------------------------------------------
+    R = Runner(name, wl, n_total, world, rank, local_rank, host_nn=args.host_nn)
+    n_sets = R.pb["nfull_total"]            # conditioning sets with n0 >= 2 over all ranks: the unit of `value`
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = G.lib.gpv_launch_count()
-    ms_total = timed(step_dev, args.steps, args.warmup)
-    launches = int(G.lib.gpv_launch_count() - launches0) - 2 * args.warmup
+    ms_total = R.timed(R.step_dev, args.steps, args.warmup)
+    launches = int(G.lib.gpv_launch_count() - launches0)
+    launches = launches * args.steps // (args.steps + args.warmup)      # timed region only
     clocks = sampler.stop()
     value = n_sets * args.steps / (ms_total * 1e-3)
-    # duration of the dominant kernel over the SAME timed region: one CUDA-event pair per launch,
-    # recorded by the library on the launching stream
-    k_count, k_total = h.kernel_time_stats(reset=True)
+    k_count, k_total = R.h.kernel_time_stats(reset=True)
     k_ms = k_total / max(k_count, 1)
-    kname = h.last_kernel_name()
-
-    # ---- e2e: the reference-facing host-buffer call createU() makes --------------------------------
-    total_packed = h.packed_len
-    n_obs = n_total
-    host_out = torch.empty(total_packed + 2 * n_obs, dtype=torch.float64).pin_memory()
-    host_nug = torch.from_numpy(nuggets).pin_memory()
-    host_tau = torch.from_numpy(nug_obs).pin_memory()
-    out_np, nug_np, tau_np = host_out.numpy(), host_nug.numpy(), host_tau.numpy()
-
-    def step_e2e():
-        h.values_packed(covType, covparms, nug_np, tau_np, zentries_tail=True, out=out_np)
+    roofline = roofline_block(R, k_ms, k_count, ms_total / args.steps, peak_tf)
+    perr, nsamp = R.parity_sample()
+    roofline["parity_max_err"] = perr
+    roofline["parity"] = f"max row-scaled |U - oracle| over {nsamp} sampled rows per rank, MAX over ranks (bar 1e-10)"
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = n_sets * e2e_steps / float(t_e2e.item())
-    h2d = 8 * nuggets.size + 8 * n_obs
-    d2h = 8 * (total_packed + 2 * n_obs)
+    em = R.e2e(e2e_steps)
+    e2e_value = n_sets / em["seconds_per_step"]
+    d2h_all = sum_over_ranks(em["d2h"], R)
+    e2e = {"value": e2e_value, "unit": "sets/s", "h2d_bytes_per_step": em["h2d"], "d2h_bytes_per_step": em["d2h"],
+           "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers; per rank: all per-location "
+                   "nuggets up, its rows' U values and its slice of Zentries down)",
+           "achieved_gbs": d2h_all / em["seconds_per_step"] / 1e9,
+           "ceiling_gbs": d2h_all / em["copy_seconds_per_step"] / 1e9,
+           "frac": em["copy_seconds_per_step"] / em["seconds_per_step"],
+           "ceiling": "the same bytes as plain pinned device-to-host copies, all ranks at once, measured in this run"}
+    if host_binding:
+        e2e["host_binding"] = host_binding
 
-    # ---- extras: loglik evals/sec (fused numerator, scalars out), other covariances ----------------
-    extras = {}
+    # likelihood: fused numerator (+ denominator terms for the pure-z layout), scalars out, one all-reduce
+    ll_steps = max(5, args.steps // 2)
+    ms_ll = R.timed(R.step_ll, ll_steps, 3)
+    llv = R.loglik_value()
+    e2e["loglik_evals_per_s"] = ll_steps / (ms_ll * 1e-3)
+    e2e["loglik"] = llv.get("loglik")
+    e2e["loglik_what"] = ("whole vecchia_likelihood (numerator + per-row denominator terms, pure-z layout), data resident "
+                          "in HBM, partial sums all-reduced; device-timed like `value`")
+    if wl["layout"] == "z":
+        out_np, nug_np, tau_np = R.e2e_bufs
+        host_z = torch.from_numpy(R.pb["z"]).pin_memory().numpy()
+        full_tau = torch.from_numpy(R.pb["nug_obs"]).pin_memory().numpy()
+        for _ in range(2):
+            R.h.loglik_z(wl["covType"], R.pb["covparms"], nug_np, full_tau, host_z)
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ll_steps):
+            R.h.loglik_z(wl["covType"], R.pb["covparms"], nug_np, full_tau, host_z)
+        R.barrier()
+        e2e["loglik_e2e_evals_per_s"] = ll_steps / R.allmax(time.perf_counter() - t0)
+        R.h.loglik_z(wl["covType"], R.pb["covparms"], nug_np, full_tau, host_z)
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ll_steps):
+            R.h.loglik_z(wl["covType"], R.pb["covparms"], None, None, None)
+        R.barrier()
+        e2e["loglik_e2e_resident_evals_per_s"] = ll_steps / R.allmax(time.perf_counter() - t0)
+        e2e["loglik_e2e_what"] = ("gpv_loglik_z per rank with host buffers (nuggets, tau, z up; 6 doubles back), and its "
+                                  "estimation-loop form (data resident on the handle, only covparms go up)")
+
+    extras = {"input_generation_s": R.t_gen, "handle_creation_s": R.t_create}
     if not args.no_extras:
-        # the same end-to-end call delivering dgCMatrix@x (compressed-column order)
         try:
-            ncols, nnz_csc, _ = h.csc_dims()
+            ncols, nnz_csc, _ = R.h.csc_dims()
             host_csc = torch.empty(nnz_csc, dtype=torch.float64).pin_memory().numpy()
+            nug_np = R.e2e_bufs[1]
+            full_tau = R.pb["nug_obs"]
             for _ in range(2):
-                h.values_csc(covType, covparms, nug_np, tau_np, out=host_csc)
-            barrier()
+                R.h.values_csc(wl["covType"], R.pb["covparms"], nug_np, full_tau, out=host_csc)
+            R.barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                h.values_csc(covType, covparms, nug_np, tau_np, out=host_csc)
-            barrier()
-            t_csc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t_csc, op=dist.ReduceOp.MAX)
-            extras["e2e_csc_sets_per_s"] = n_sets * e2e_steps / float(t_csc.item())
+                R.h.values_csc(wl["covType"], R.pb["covparms"], nug_np, full_tau, out=host_csc)
+            R.barrier()
+            e2e["csc_sets_per_s"] = n_sets * e2e_steps / R.allmax(time.perf_counter() - t0)
             del host_csc
-        except G.GpvError as e:                      # duplicate U rows in a set: triplet route only
-            extras["e2e_csc_sets_per_s"] = None
-        ll_steps = max(5, args.steps // 2)
-
-        def step_ll():
-            h.u_dev(covType, covparms, d_nug.data_ptr(), None, d_zord=d_z.data_ptr(), skip_rows=pb["skip_rows"],
-                    d_loglik=d_ll.data_ptr(), stream=stream)
-            if world > 1:
-                shard.allreduce_loglik(d_ll)          # 3 doubles over NCCL: the path's only collective
-        ms_ll = timed(step_ll, ll_steps, 3)
-        # pure `z` layout: the same launch also accumulates the denominator terms, so this is the
-        # whole vecchia_likelihood (R/vecchia_likelihood.R:14-27) with the data resident in HBM
-        extras["loglik_evals_per_s"] = ll_steps / (ms_ll * 1e-3)
-        extras["loglik_sets_per_s"] = n_sets * ll_steps / (ms_ll * 1e-3)
-        parts = [float(v) for v in d_ll.cpu().tolist()]
-        tau_terms = float(np.sum(z * z / nug_obs)), float(np.sum(np.log(nug_obs)))
-        qn, ldn, qd, ldd = parts[0] + tau_terms[0], parts[1] + tau_terms[1], parts[3], parts[4]
-        extras["loglik_parts"] = dict(quadform_num=qn, logdet_num=ldn, quadform_denom=qd, logdet_denom=ldd, nfail=parts[2])
-        if wl["layout"] == "z":
-            extras["loglik_value"] = -0.5 * (ldn - ldd + qn - qd + n_total * float(np.log(2 * np.pi)))
-        if wl["layout"] == "z":
-            # estimation loop: data and nuggets resident on the handle, only covparms go up (gpv_loglik_z
-            # with NULL vectors), 6 doubles come back
-            try:
-                h.loglik_z(covType, covparms, nug_np, tau_np, z)
-                barrier()
-                t0 = time.perf_counter()
-                for _ in range(ll_steps):
-                    r_res = h.loglik_z(covType, covparms, None, None, None)
-                barrier()
-                t_res = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-                if world > 1:
-                    dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-                extras["loglik_e2e_resident_evals_per_s"] = ll_steps / float(t_res.item())
-            except G.GpvError:
-                pass
-        if wl["layout"] == "z":
-            # end-to-end likelihood call with host buffers (nuggets, tau, z up; 6 doubles back)
-            host_z = torch.from_numpy(z).pin_memory().numpy()
-            for _ in range(2):
-                r_ll = h.loglik_z(covType, covparms, nug_np, tau_np, host_z)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(ll_steps):
-                r_ll = h.loglik_z(covType, covparms, nug_np, tau_np, host_z)
-            barrier()
-            extras["loglik_e2e_evals_per_s"] = ll_steps / (time.perf_counter() - t0)
-            extras["loglik_e2e_value_rank0_shard"] = r_ll["loglik"] if world == 1 else None
-        if args.workload == "cfg2":
+        except G.GpvError:                      # duplicate U rows in a set: triplet route only
+            e2e["csc_sets_per_s"] = None
+        if name == "cfg2":
             per = {}
-            rng_ = float(covparms[1])
+            rng_ = float(R.pb["covparms"][1])
             for tag, ct, cp in (("nu0.5", "matern", [SIG2, rng_, 0.5]), ("nu2.5", "matern", [SIG2, rng_, 2.5]),
                                 ("general_nu0.8", "matern", [SIG2, rng_, 0.8]), ("general_nu1.3", "matern", [SIG2, rng_, 1.3]),
                                 ("esqe", "esqe", [1.0, rng_, 0.5, rng_])):
                 cpa = np.array(cp)
-
-                def fn(ct=ct, cpa=cpa):
-                    h.u_dev(ct, cpa, d_nug.data_ptr(), d_out.data_ptr(), packed=False, stream=stream)
-                ms = timed(fn, ll_steps, 3)
+                ms = R.timed(lambda ct=ct, cpa=cpa: R.step_dev(ct, cpa), ll_steps, 3)
                 per[tag] = n_sets * ll_steps / (ms * 1e-3)
-            extras["sets_per_s_other_covariances"] = per
-
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
-    F = flops_per_set(p, d, wl["tag"])
-    B = bytes_per_set(p, d)
-    peak_tf = C.c_double(0)
-    G._lib.check(G.lib.gpv_measure_fp64_peak(local_rank, C.byref(peak_tf)))
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        hbm_src = "MEASURED_PEAKS.json"
-    except Exception:
-        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-    nfull_rank = pb["nfull_rank"]
-    achieved_tf = F * nfull_rank / (k_ms * 1e-3) / 1e12
-    roofline = {
-        "bound": "fp64", "kernel": kname, "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf.value,
-        "peak_source": "fp64 FMA peak from a DFMA micro-kernel in this run (gpv_measure_fp64_peak); "
-                       "MEASURED_PEAKS.json has HBM and bf16 only",
-        "flops_per_set": F, "sets_per_launch": nfull_rank, "kernel_ms": k_ms, "kernel_launches_timed": k_count,
-        "kernel_share_of_step": k_ms / (ms_total / args.steps),
-        "hbm": {"achieved": B * nfull_rank / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": B * nfull_rank / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_set": B, "peak_source": hbm_src},
-        "traffic": None,
-    }
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof) and args.workload == "cfg2":
-        try:
-            pj = json.load(open(prof))
-            roofline["traffic"] = pj.get("dram_bytes_per_launch")
-            roofline["fp64_pipe_active_pct_ncu"] = pj.get("fp64_pipe_pct_of_peak_active")
-            if pj.get("note"):
-                roofline["ncu_note"] = pj["note"]
-        except Exception:
-            pass
+            roofline["sets_per_s_other_covariances"] = per
 
     cpu = None
     if getattr(bind_to_gpu_cpus, "unbound", None):
         os.sched_setaffinity(0, bind_to_gpu_cpus.unbound)
-    if rank == 0 and not args.no_cpu_baseline:
-        full = (revNN != 0).sum(axis=1) >= 2          # time the full sets only (the unit of `value`)
-        rate, cores, sample = cpu_reference_rate(locs, revNN[full], revCond[full], rb, nuggets, covparms, covType=covType)
-        cpu = {"value": rate, "unit": "sets/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        full = (R.pb["revNN"] != 0).sum(axis=1) >= 2
+        cpu = cpu_baseline_block(wl, n_total, R.pb, full)
+    R.close()
+    del R
+    torch.cuda.empty_cache()
+
+    # ---- north star: cfg3, n = 1e7, general nu, strong scaling -------------------------------------------------
+    if north is not None:
+        if getattr(bind_to_gpu_cpus, "unbound", None) and world > 1:
+            bind_to_gpu_cpus(local_rank)
+        N3 = Runner("cfg3", north, north["n"], world, rank, local_rank, host_nn=args.host_nn)
+        sets3 = N3.pb["nfull_total"]
+        steps3 = max(5, min(args.steps, 10))
+        ms3 = N3.timed(N3.step_dev, steps3, 3)
+        kc3, kt3 = N3.h.kernel_time_stats(reset=True)
+        r3 = roofline_block(N3, kt3 / max(kc3, 1), kc3, ms3 / steps3, peak_tf)
+        r3.update(workload=config["north_star_workload"], n=north["n"], scaling="strong", value=sets3 * steps3 / (ms3 * 1e-3),
+                  value_unit="sets/s", ms_per_step=ms3 / steps3, steps=steps3)
+        perr3, nsamp3 = N3.parity_sample()
+        r3["parity_max_err"] = perr3
+        r3["parity"] = f"max row-scaled |U - oracle| over {nsamp3} sampled rows per rank, MAX over ranks (bar 1e-10)"
+        ms3l = N3.timed(N3.step_ll, steps3, 3)
+        ll3 = N3.loglik_value()
+        r3["loglik_evals_per_s"] = steps3 / (ms3l * 1e-3)
+        r3["loglik"] = ll3.get("loglik")
+        r3["loglik_nfail"] = ll3.get("nfail")
+        try:
+            gold = json.load(open(GOLD_LL)).get(f"cfg3_n{north['n']}_nu{north['nu']}")
+        except Exception:
+            gold = None
+        if gold is not None and ll3.get("loglik") is not None:
+            r3["loglik_rel_err_vs_n1"] = abs(ll3["loglik"] - gold) / abs(gold)     # bar 1e-8
+        em3 = N3.e2e(3)
+        d2h3 = sum_over_ranks(em3["d2h"], N3)
+        e2e["cfg3"] = {"value": sets3 / em3["seconds_per_step"], "unit": "sets/s", "h2d_bytes_per_step": em3["h2d"],
+                       "d2h_bytes_per_step": em3["d2h"], "achieved_gbs": d2h3 / em3["seconds_per_step"] / 1e9,
+                       "ceiling_gbs": d2h3 / em3["copy_seconds_per_step"] / 1e9,
+                       "frac": em3["copy_seconds_per_step"] / em3["seconds_per_step"],
+                       "loglik_evals_per_s": r3["loglik_evals_per_s"]}
+        roofline["cfg3"] = r3
+        extras["cfg3_input_generation_s"] = N3.t_gen
+        extras["cfg3_handle_creation_s"] = N3.t_create
+        N3.close()
 
     if rank == 0:
         line = {
@@ -558,13 +814,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": "sets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers)"},
-            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
-            "input_generation_s": t_gen,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
         print(json.dumps(line))
-    h.close()
     if world > 1:
         dist.destroy_process_group()
 

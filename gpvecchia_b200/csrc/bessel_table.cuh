@@ -23,10 +23,10 @@
 namespace gpv {
 
 #ifndef GPV_TAB_DEG
-#define GPV_TAB_DEG 19
+#define GPV_TAB_DEG 10
 #endif
 #ifndef GPV_TAB_SUBBITS
-#define GPV_TAB_SUBBITS 1
+#define GPV_TAB_SUBBITS 2
 #endif
 constexpr int kTabDeg = GPV_TAB_DEG;
 constexpr int kTabSubBits = GPV_TAB_SUBBITS;   // 2^bits intervals per octave of w
@@ -35,10 +35,14 @@ constexpr int kTabOctaves = 64;             // covered range of w below its maxi
 constexpr double kTabSSplit = 16.0;         // s >= split: table holds exp(s) * cov
 constexpr int kTabStride = kTabOctaves * kTabSub;   // intervals per coefficient row
 // Coefficient-major storage: coefficient k of interval i sits at coef[k * kTabStride + i] (every
-// offset an immediate).  The gather is bound by the L1 data pipe (94 % busy, profiles/): few, wide
-// intervals keep the lanes of a warp on few cache lines.  Measured at n = 1e6, m = 30 (ms per
-// launch): (sub_bits, degree) = (3,11) 5.50, (2,14) 5.34, (1,19) 5.14; 16-byte paired loads
-// (1,19) 5.57; interval-major rows (5,7) 7.03.
+// offset an immediate).  The pair stage of the general branch is bound by these gathers (L1 / shared data pipe
+// 85-87 % busy, 2.2-2.4 wavefronts per 8-byte gather, profiles/r01_*, r02_*), so what counts is the NUMBER of
+// coefficients.  Round 1 used (sub_bits, degree) = (1, 19); measured against mpmath, the error that matters for
+// a covariance MATRIX -- absolute, relative to sigma^2 -- is already at the rounding floor of the Horner
+// evaluation (2e-15) with (2, 10), (3, 8) or (4, 7), for any nu in [0.05, 10] and s up to the exp split
+// (tools/tab_degree_scan.py); relative accuracy holds to 3e-15 for s <= 3 and degrades as exp(s) beyond, where
+// the covariance itself is below 0.05 sigma^2.  (2, 10): 11 gathers instead of 20, and 24 octaves of w fit the
+// 8.4 KB shared-memory window of the band kernels.
 __host__ __device__ constexpr int tab_coef_index(int k, int i) { return k * kTabStride + i; }
 
 __host__ __device__ inline int hi32_of(double x) {
@@ -239,9 +243,9 @@ __device__ __forceinline__ double cov_general_fast(double r2, int idx, const Cov
   return acc;
 }
 // The same polynomial with the coefficients read from the shared-memory window of the table (u_band.cuh):
-// `cf` points at interval j of a coefficient-major array with GW intervals per row.  A warp's lanes sit on a
-// dozen neighbouring intervals, i.e. on different banks: about one wavefront per coefficient, where the
-// global-memory gather costs 2.4 (profiles/r02_u_band_general_*).
+// `cf` points at interval j of a coefficient-major array with GW intervals per row.  Measured: 2.2 wavefronts per
+// gather (two half-warps), against 2.4 from global memory through a 29 KB L1 -- the gain of the window is
+// that it cannot be evicted by the streams (profiles/r02b_u_band_general_*).
 template <int GW>
 __device__ __forceinline__ double cov_general_fast_shared(double r2, const double* __restrict__ cf) {
   const int hi = __double2hiint(r2), lo = __double2loint(r2);
@@ -249,10 +253,15 @@ __device__ __forceinline__ double cov_general_fast_shared(double r2, const doubl
   const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
   const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
   const double v = m - mc;
-  double acc = cf[kTabDeg * GW];
+  // even / odd halves in u = v^2: two independent Horner chains instead of one of deg + 1 terms
+  constexpr int KE = (kTabDeg / 2) * 2, KO = ((kTabDeg - 1) / 2) * 2 + 1;   // highest even / odd power
+  const double u = v * v;
+  double ev = cf[KE * GW], od = cf[KO * GW];
 #pragma unroll
-  for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, cf[k * GW]);
-  return acc;
+  for (int k = KE - 2; k >= 0; k -= 2) ev = fma(ev, u, cf[k * GW]);
+#pragma unroll
+  for (int k = KO - 2; k >= 1; k -= 2) od = fma(od, u, cf[k * GW]);
+  return fma(od, v, ev);
 }
 // Slow path (per lane correct for anything): zero distance, far pairs (exp split), arguments outside
 // the table, NaN.

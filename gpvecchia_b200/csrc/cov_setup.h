@@ -28,7 +28,10 @@ inline void nu_constants(double nu, double sig2, CovTable* t) {
 
 // table range: the top kTabOctaves octaves of w below the squared bounding-box diagonal w_max; for
 // s = d / range >= kTabSSplit the table holds exp(+s) cov (w_split is an interval edge)
-inline void general_table_range(double range, double w_max, CovTable* tp) {
+// win_top_exp: biased exponent of the highest octave of w the shared-memory window should hold (from the
+// handle's histogram of neighbour distances), or < 0: the window ends at the top of the table.
+constexpr int kTabWindow = 24 * kTabSub;            // intervals in the window: 24 octaves of w (4096 : 1 in distance)
+inline void general_table_range(double range, double w_max, CovTable* tp, int win_top_exp = -1) {
   CovTable& t = *tp;
   double wmax = (w_max > 0.0 && std::isfinite(w_max)) ? w_max : 1.0;
   const int code_hi = hi32_of(wmax) >> (20 - kTabSubBits);
@@ -40,6 +43,15 @@ inline void general_table_range(double range, double w_max, CovTable* tp) {
   const double ws = (kTabSSplit * range) * (kTabSSplit * range);
   const int code_split = hi32_of(ws) >> (20 - kTabSubBits);
   t.w_split = from_hilo(code_split << (20 - kTabSubBits), 0);
+  int win_end = idx0 + nint;                          // one past the last interval code of the window
+  if (win_top_exp >= 0) {
+    const int e = ((win_top_exp + 1) << kTabSubBits);
+    if (e < win_end) win_end = e;
+  }
+  int win0 = win_end - kTabWindow - idx0;
+  if (win0 > nint - kTabWindow) win0 = nint - kTabWindow;
+  if (win0 < 0) win0 = 0;
+  t.win0 = win0;
 }
 
 }  // namespace gpv

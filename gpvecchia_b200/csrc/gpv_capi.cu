@@ -104,15 +104,19 @@ const KernelEntry* select_kernel(int p, int d, bool general) {
 // column-major 1-based revNN (0 = missing) -> row-major 0-based (-1 = missing), shard rows only;
 // also per-row n0.
 __global__ void prep_nn_kernel(const int32_t* __restrict__ nn_cm, int64_t ld, int p,
-                               int64_t row_begin, int64_t nrows, int32_t* __restrict__ nn_rm,
-                               int64_t* __restrict__ n0_out) {
+                               int64_t row_begin, int64_t nrows, int64_t Nlocs, int32_t* __restrict__ nn_rm,
+                               int64_t* __restrict__ n0_out, int* __restrict__ bad) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
   int n0 = 0;
   for (int j = 0; j < p; ++j) {
+    // 1-based ids; 0 (createU.R:146-147), NA_integer_ (INT_MIN) and any other non-positive value are "missing",
+    // like gpv_whichCondOnLatent reads them; an id beyond Nlocs is an error (the reference would read out of bounds)
     const int32_t v = nn_cm[(row_begin + r) + (int64_t)j * ld];
-    nn_rm[r * p + j] = v - 1;           // 0 -> -1 (missing)
-    n0 += (v != 0);
+    const bool present = v > 0;
+    if (present && (int64_t)v > Nlocs) atomicOr(bad, 1);
+    nn_rm[r * p + j] = present ? v - 1 : -1;
+    n0 += present;
   }
   n0_out[r] = n0;
 }
@@ -143,13 +147,99 @@ __global__ void gather_cond_rows_kernel(const uint64_t* __restrict__ cond, const
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < nsets) cond_full[s] = cond[rowmap[s]];
 }
-// zloc[i] = z of location i (0 where unobserved): lets the set kernel gather z like a nugget
+// zloc[i] = z of location i (0 where unobserved): lets the set kernel gather z like a nugget.  With a locality
+// order (below) entry i is the location order[i].
 __global__ void expand_z_kernel(const double* __restrict__ zord, const int32_t* __restrict__ obsrank,
-                                int64_t Nlocs, double* __restrict__ zloc) {
+                                const int32_t* __restrict__ order, int64_t Nlocs, double* __restrict__ zloc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Nlocs) return;
-  const int r = obsrank[i];
+  const int r = obsrank[order ? order[i] : i];
   zloc[i] = r >= 0 ? zord[r] : 0.0;
+}
+// ---- locality layer (large N) -----------------------------------------------------------------------------
+// The index order of the locations is an ORDERING (maxmin, random ...), not a spatial one: the 31 neighbours of a
+// row are 31 random addresses in locs / nuggets, and once those arrays outgrow the L2 (n >= 2e6) every set pays
+// ~60 DRAM sectors for them (profiles/r02_*_n8e6: 2.1 KB read per set against 170 B compulsory).  For large N
+// the handle therefore keeps (i) a replica of the per-location data sorted along a Morton curve, with the
+// neighbour ids renamed to positions in it -- a set's points then sit in a few neighbouring lines -- and (ii)
+// processes the rows of each output chunk in Morton order of their own location, so that the sets in flight at
+// any time work on one compact region that the L2 holds.  Results are written by row as before: the output is
+// bit-identical, only the order of work inside a launch changes.
+__global__ void morton_key_kernel(const double* __restrict__ locs, int64_t N, int d, const double* __restrict__ box,
+                                  const int32_t* __restrict__ ids, int64_t id_base, int64_t count,
+                                  const int64_t* __restrict__ chunk_set, int nchunks, uint64_t* __restrict__ keys,
+                                  int32_t* __restrict__ vals) {
+  // key of entry i: Morton code of location (ids ? id_base + ids[i] : id_base + i); box = {min_c, 1/extent_c};
+  // with a chunk table the chunk number of entry i goes into the high word (rows never leave their chunk)
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t loc = id_base + (ids ? (int64_t)ids[i] : i);
+  const int dd = d < 3 ? d : 3;
+  const int bits = (dd == 1) ? 30 : (dd == 2 ? 16 : 10);
+  uint32_t code = 0, q[3] = {0, 0, 0};
+  for (int c = 0; c < dd; ++c) {
+    double t = (locs[loc * d + c] - box[2 * c]) * box[2 * c + 1];
+    t = (t >= 0.0) ? t : 0.0;                    // NaN coordinates sort first
+    t = (t <= 1.0) ? t : 1.0;
+    q[c] = (uint32_t)(t * (double)((1u << bits) - 1u));
+  }
+  for (int b = bits - 1; b >= 0; --b)
+    for (int c = 0; c < dd; ++c) code = (code << 1) | ((q[c] >> b) & 1u);
+  uint64_t hi = 0;
+  if (chunk_set) { int c = 0; while (c + 1 < nchunks && i >= chunk_set[c + 1]) ++c; hi = (uint64_t)c; }
+  keys[i] = (hi << 32) | code;
+  vals[i] = (int32_t)i;
+}
+// histogram of the exponents of the squared distances between a row's own point and its neighbours: places the
+// shared-memory window of the general-nu coefficient table (cov_setup.h) where this handle's distances are
+__global__ void r2_exponent_hist_kernel(const double* __restrict__ locs, const int32_t* __restrict__ nn, int64_t nrows,
+                                        int p, int d, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t self = nn[r * p + p - 1];
+    if (self < 0) continue;
+    for (int j = 0; j < p - 1; ++j) {
+      const int32_t id = nn[r * p + j];
+      if (id < 0) continue;
+      double w = 0.0;
+      for (int c = 0; c < d; ++c) { const double t = locs[(int64_t)self * d + c] - locs[(int64_t)id * d + c]; w = fma(t, t, w); }
+      if (w > 0.0 && w < 1.0e300) atomicAdd(&sh[(__double2hiint(w) >> 20) & 2047], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+__global__ void invert_perm_kernel(const int32_t* __restrict__ order, int64_t N, int32_t* __restrict__ inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) inv[order[i]] = (int32_t)i;
+}
+__global__ void gather_locs_kernel(const double* __restrict__ locs, const int32_t* __restrict__ order, int64_t N, int d,
+                                   double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t o = order[i];
+  for (int c = 0; c < d; ++c) out[i * d + c] = locs[o * d + c];
+}
+__global__ void gather_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ order, int64_t N,
+                                  double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = src[order[i]];
+}
+// set s of the processing order = set perm[s] of the row order: its row number and its (renamed) neighbour ids
+__global__ void permute_sets_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ rowmap_in,
+                                    const int32_t* __restrict__ nn_in, const int32_t* __restrict__ inv, int64_t nsets,
+                                    int p, int32_t* __restrict__ rowmap_out, int32_t* __restrict__ nn_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsets * p) return;
+  const int64_t s = i / p;
+  const int j = (int)(i - s * p);
+  const int64_t src = perm[s];
+  const int32_t id = nn_in[src * p + j];
+  nn_out[i] = id >= 0 ? inv[id] : -1;
+  if (j == 0) rowmap_out[s] = rowmap_in ? rowmap_in[src] : (int32_t)src;
 }
 // nuggets.all.ord / nuggets.ord of a scalar nugget (createU.R:70-78): the nugget at observed locations,
 // 0 at the others
@@ -401,6 +491,7 @@ struct gpv_handle {
   bool have_obs = false;
   int64_t packed_len = 0;
   double w_max = 0.0;                 // squared diameter of the bounding box of locs
+  int win_top_exp = -1;               // biased exponent of the highest octave of squared neighbour distances (general-nu window)
   // resident, parameter-free
   double* d_locs = nullptr;           // [Nlocs][d]
   int32_t* d_nn = nullptr;            // [nrows][p]
@@ -424,9 +515,18 @@ struct gpv_handle {
   int32_t* d_nn_full = nullptr;       // [nfull][p]
   uint64_t* d_cond_full = nullptr;    // [nfull]
   int32_t* d_trivlist = nullptr;      // [ntriv] rows with n0 <= 1
+  // locality layer (large N, see morton_key_kernel): sorted replica of the per-location data; with it the set
+  // list above (d_rowmap / d_nn_full / d_cond_full) exists for every layout and is in processing order
+  bool locality = false;
+  bool mapped = false;                // the set kernel reads the set list (split || locality)
+  int32_t* d_order = nullptr;         // [Nlocs] location held at position i of the sorted replica
+  double* d_locs_s = nullptr;         // [Nlocs][d] sorted replica of locs
+  double* d_nug_s = nullptr;          // [Nlocs] per call: nuggets in replica order
+  double* d_zloc_rows = nullptr;      // [Nlocs] z per location in the ORIGINAL order (n0 <= 1 rows of a split layout)
   // per-call scratch (allocated lazily, reused)
   double* d_nuggets = nullptr;        // [Nlocs]
-  double* d_tau = nullptr;            // [n_obs]
+  double* d_tau = nullptr;            // [tau_cap] (with d_zent [2 tau_cap])
+  int64_t tau_cap = 0;
   double* d_zord = nullptr;           // [n_obs]
   double* d_zloc = nullptr;           // [Nlocs] z per location for the fused likelihood
   int* d_flag = nullptr;
@@ -471,7 +571,7 @@ static void free_handle(gpv_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
   cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
-  cudaFree(h->d_trivlist); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
+  cudaFree(h->d_trivlist); cudaFree(h->d_order); cudaFree(h->d_locs_s); cudaFree(h->d_nug_s); cudaFree(h->d_zloc_rows); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
   cudaFree(h->d_zloc); cudaFree(h->d_flag); cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
   cudaFree(h->d_first_fail); cudaFree(h->d_table);
@@ -499,9 +599,10 @@ static gpv_status upload_cond(gpv_handle* h, const void* host) {
                                                                         h->shard_arrays ? 0 : h->row_begin,
                                                                         h->nrows, h->d_cond);
     g_launches++;
-    if (h->split && h->nfull > 0) {
-      gather_cond_rows_kernel<<<grid_for(h->nfull, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap, h->nfull,
-                                                                              h->d_cond_full);
+    const int64_t nmapped = h->split ? h->nfull : h->nrows;
+    if (h->mapped && nmapped > 0) {
+      gather_cond_rows_kernel<<<grid_for(nmapped, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap, nmapped,
+                                                                             h->d_cond_full);
       g_launches++;
     }
     int not_pure = 0;
@@ -525,7 +626,10 @@ extern "C" gpv_status gpv_set_revcond(gpv_handle* h, const void* revCond, gpv_co
   // changes revCond for one U_NZentries call only and still assembles with U.prep's indices.  Freeze the
   // compressed-column structure before the first overwrite (gpv_csc.inc keeps its own copy of the mask).
   if (h->have_obs && h->cond_uploaded && !h->csc_ready) (void)ensure_csc(h);
-  if (h->nrows == 0) return GPV_OK;
+  if (h->nrows == 0) {                  // an empty shard (more devices than balanced cuts) does not veto a pure-z layout
+    h->pure_z = h->have_obs && h->n_obs == h->Nlocs;
+    return GPV_OK;
+  }
   if (cond_type == GPV_COND_RLOGICAL_I32) return upload_cond<int32_t>(h, revCond);
   if (cond_type == GPV_COND_F64) return upload_cond<double>(h, revCond);
   return fail(GPV_ERR_ARG, "gpv_set_revcond: unknown cond_type %d", (int)cond_type);
@@ -630,6 +734,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaMalloc(&h->d_first_fail, sizeof(long long)));
 
   // locs: upload column-major, transpose on device; bounding box on the host copy (once)
+  double box[6] = {0, 0, 0, 0, 0, 0};   // {min, 1 / extent} of the first three coordinates (locality keys)
   {
     double* tmp = nullptr;
     H_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)Nlocs * d));
@@ -647,6 +752,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       const double* col = locs + (size_t)c * Nlocs;
       for (int64_t i = 0; i < Nlocs; ++i) { mn = col[i] < mn ? col[i] : mn; mx = col[i] > mx ? col[i] : mx; }
       w += (mx - mn) * (mx - mn);
+      if (c < 3) { box[2 * c] = mn; box[2 * c + 1] = (mx > mn) ? 1.0 / (mx - mn) : 0.0; }
     }
     h->w_max = w;
   }
@@ -661,7 +767,8 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     size_t scan_bytes = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, revNNarray, sizeof(int32_t) * (size_t)ld * p, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-      prep_nn_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, ld, p, shard_arrays ? 0 : row_begin, h->nrows, h->d_nn, n0);
+      cudaMemsetAsync(h->d_flag, 0, sizeof(int), h->stream);
+      prep_nn_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(tmp, ld, p, shard_arrays ? 0 : row_begin, h->nrows, Nlocs, h->d_nn, n0, h->d_flag);
       g_launches++;
       e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, n0, h->d_row_off, (int)h->nrows, h->stream);
     }
@@ -671,9 +778,16 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       g_launches++;
     }
     int64_t last_off = 0, last_n0 = 0;
+    int bad_id = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad_id, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_off, h->d_row_off + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&last_n0, n0 + (h->nrows - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && bad_id) {
+      cudaFree(tmp); cudaFree(n0); cudaFree(scan_tmp);
+      free_handle(h);
+      return fail(GPV_ERR_ARG, "gpv_create: revNNarray holds an id greater than Nlocs=%lld", (long long)Nlocs);
+    }
     // row classes
     int32_t *is_full = nullptr, *is_triv = nullptr, *pos_full = nullptr, *pos_triv = nullptr;
     void* scan2 = nullptr;
@@ -700,6 +814,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       h->nfull = (int64_t)lf + lpf;
       h->ntriv = (int64_t)lt + lpt;
       h->split = h->ntriv * 64 >= h->nrows;
+      h->mapped = h->split;
       if (h->split) {
         e = cudaMalloc(&h->d_rowmap, sizeof(int32_t) * (size_t)(h->nfull > 0 ? h->nfull : 1));
         if (e == cudaSuccess) e = cudaMalloc(&h->d_trivlist, sizeof(int32_t) * (size_t)(h->ntriv > 0 ? h->ntriv : 1));
@@ -778,6 +893,94 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       h->chunk_row[c] = row;
     }
   }
+  // where are this handle's squared neighbour distances?  (general-nu window; a few microseconds per million rows)
+  if (h->nrows > 0) {
+    unsigned long long* d_hist = nullptr;
+    std::vector<unsigned long long> hist(2048, 0ull);
+    H_TRY(cudaMalloc(&d_hist, sizeof(unsigned long long) * 2048));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 2048, h->stream);
+    if (e == cudaSuccess) {
+      r2_exponent_hist_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->d_locs, h->d_nn, h->nrows, p, d, d_hist);
+      g_launches++;
+      e = cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * 2048, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_hist);
+    H_TRY(e);
+    unsigned long long total = 0, acc = 0;
+    for (auto v : hist) total += v;
+    if (total > 0) {
+      // the 24-octave window sits around the MEDIAN squared neighbour distance w50: up to 2^8.x w50 (set diameters of
+      // rows down to ~1/40 of the way into the ordering, whose neighbourhoods are that much wider) and down to
+      // 2^-15.x w50 (pairs 200 times closer than the typical neighbour: a per-mille event per set)
+      int med = 0;
+      while (med < 2047 && 2 * (acc + hist[med]) < total) { acc += hist[med]; ++med; }
+      h->win_top_exp = med + 8;
+    }
+  }
+  // locality layer: on for large N (per-location data beyond ~48 MB no longer sit in the L2 next to the streams);
+  // GPV_LOCALITY=1 / 0 forces it on / off (tests run both ways on small problems)
+  {
+    // measured (profiles/r02_kbench_locality.log): 13 % at n = 8e6 (the per-location data no longer fit the L2),
+    // still 3 % at n = 1e6 (L1 hits); below ~1e5 rows a launch is latency bound and the extra gather is not worth it
+    bool want = Nlocs >= 131072;
+    if (const char* env = std::getenv("GPV_LOCALITY")) { if (env[0] == '1') want = true; else if (env[0] == '0') want = false; }
+    const int64_t nsets = h->split ? h->nfull : h->nrows;
+    if (want && nsets > 0) {
+      uint64_t *k_in = nullptr, *k_out = nullptr;
+      int32_t *v_in = nullptr, *v_out = nullptr, *inv = nullptr, *rowmap2 = nullptr, *nn2 = nullptr;
+      double* d_box = nullptr;
+      int64_t* d_chunks = nullptr;
+      void* tmp = nullptr;
+      size_t tmp_bytes = 0;
+      const int64_t cap = Nlocs > nsets ? Nlocs : nsets;
+      cudaError_t e = cudaMalloc(&k_in, sizeof(uint64_t) * (size_t)cap);
+      if (e == cudaSuccess) e = cudaMalloc(&k_out, sizeof(uint64_t) * (size_t)cap);
+      if (e == cudaSuccess) e = cudaMalloc(&v_in, sizeof(int32_t) * (size_t)cap);
+      if (e == cudaSuccess) e = cudaMalloc(&v_out, sizeof(int32_t) * (size_t)cap);
+      if (e == cudaSuccess) e = cudaMalloc(&inv, sizeof(int32_t) * (size_t)Nlocs);
+      if (e == cudaSuccess) e = cudaMalloc(&d_box, sizeof(box));
+      if (e == cudaSuccess) e = cudaMalloc(&d_chunks, sizeof(h->chunk_set));
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_order, sizeof(int32_t) * (size_t)Nlocs);
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_locs_s, sizeof(double) * (size_t)Nlocs * d);
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_nug_s, sizeof(double) * (size_t)Nlocs);
+      if (e == cudaSuccess) e = cudaMalloc(&rowmap2, sizeof(int32_t) * (size_t)nsets);
+      if (e == cudaSuccess) e = cudaMalloc(&nn2, sizeof(int32_t) * (size_t)nsets * p);
+      if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)cap, 0, 40, h->stream);
+      if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_box, box, sizeof(box), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_chunks, h->chunk_set, sizeof(h->chunk_set), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) {
+        // (i) locations along the curve
+        morton_key_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(h->d_locs, Nlocs, d, d_box, nullptr, 0, Nlocs, nullptr, 0, k_in, v_in);
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, h->d_order, (int)Nlocs, 0, 32, h->stream);
+        invert_perm_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(h->d_order, Nlocs, inv);
+        gather_locs_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(h->d_locs, h->d_order, Nlocs, d, h->d_locs_s);
+        g_launches += 4;
+      }
+      if (e == cudaSuccess) {
+        // (ii) the sets of every output chunk in Morton order of their own location (row r owns location row_begin + r)
+        morton_key_kernel<<<grid_for(nsets, 256), 256, 0, h->stream>>>(h->d_locs, Nlocs, d, d_box, h->split ? h->d_rowmap : nullptr,
+                                                                       row_begin, nsets, d_chunks, h->nchunks, k_in, v_in);
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)nsets, 0, 40, h->stream);
+        permute_sets_kernel<<<grid_for(nsets * p, 256), 256, 0, h->stream>>>(v_out, h->split ? h->d_rowmap : nullptr,
+                                                                              h->split ? h->d_nn_full : h->d_nn, inv, nsets, p, rowmap2, nn2);
+        g_launches += 3;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      }
+      cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(inv); cudaFree(d_box); cudaFree(d_chunks); cudaFree(tmp);
+      if (e == cudaSuccess) {
+        cudaFree(h->d_rowmap); cudaFree(h->d_nn_full);
+        h->d_rowmap = rowmap2; h->d_nn_full = nn2;
+        if (!h->d_cond_full) e = cudaMalloc(&h->d_cond_full, sizeof(uint64_t) * (size_t)nsets);
+        h->locality = true;
+        h->mapped = true;
+      } else {
+        cudaFree(rowmap2); cudaFree(nn2);
+      }
+      H_TRY(e);
+    }
+  }
   *out = h;
   gpv_status st = gpv_set_revcond(h, revCond, cond_type);
   h->cond_uploaded = true;
@@ -828,7 +1031,7 @@ struct CovSetup {
 };
 
 static gpv_status setup_cov(const char* covType, const double* covparms, int ncov, double w_max,
-                            CovSetup* cs) {
+                            CovSetup* cs, int win_top_exp = -1) {
   if (!covType || !covparms) return fail(GPV_ERR_ARG, "covType/covparms is null");
   UParams& q = cs->q;
   std::memset(&q, 0, sizeof(q));
@@ -846,7 +1049,7 @@ static gpv_status setup_cov(const char* covType, const double* covparms, int nco
       cs->needs_table = true;
       CovTable& t = q.tab;
       nu_constants(nu, sig2, &t);
-      general_table_range(range, w_max, &t);
+      general_table_range(range, w_max, &t, win_top_exp);
     }
   } else if (std::strcmp(covType, "esqe") == 0) {
     if (ncov < 4) return fail(GPV_ERR_ARG, "esqe needs covparms = (sig2_1, r1, sig2_2, r2)");
@@ -894,18 +1097,31 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
   q.nsets = set_count;
   q.set_base = set_begin;
-  q.rowmap = h->split ? h->d_rowmap + set_begin : nullptr;
-  q.locs = h->d_locs; q.nuggets = d_nuggets;
-  q.nn = (h->split ? h->d_nn_full : h->d_nn) + set_begin * h->p;
-  q.cond = (h->split ? h->d_cond_full : h->d_cond) + set_begin;
+  q.rowmap = h->mapped ? h->d_rowmap + set_begin : nullptr;
+  q.locs = h->locality ? h->d_locs_s : h->d_locs;
+  q.nuggets = d_nuggets;
+  if (h->locality) {
+    if (set_begin == 0) {               // once per call (the chunks of a call share it)
+      gather_f64_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_nuggets, h->d_order, h->Nlocs, h->d_nug_s);
+      g_launches++;
+    }
+    q.nuggets = h->d_nug_s;
+  }
+  q.nn = (h->mapped ? h->d_nn_full : h->d_nn) + set_begin * h->p;
+  q.cond = (h->mapped ? h->d_cond_full : h->d_cond) + set_begin;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
   q.zloc = nullptr; q.full_z = 0; q.skip_rows = skip_rows;
   if (want_loglik) {
     // z per location, expanded once per call so the set kernel can prefetch it like a nugget
     if (!h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
-    expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, h->Nlocs, h->d_zloc);
+    expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, h->locality ? h->d_order : nullptr, h->Nlocs, h->d_zloc);
     g_launches++;
     q.zloc = h->d_zloc;
+    if (h->locality && h->split && h->ntriv > 0) {
+      if (!h->d_zloc_rows) CUDA_TRY(cudaMalloc(&h->d_zloc_rows, sizeof(double) * (size_t)h->Nlocs));
+      expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, nullptr, h->Nlocs, h->d_zloc_rows);
+      g_launches++;
+    }
     q.full_z = (h->pure_z && skip_rows == 0) ? 1 : 0;
   }
   q.partials = want_loglik ? h->d_partials : nullptr;
@@ -937,7 +1153,10 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   if (h->split && h->ntriv > 0 && set_begin == 0) {
     int64_t wt = (h->ntriv + 255) / 256;
     const int tb = (int)(wt < kTrivBlocks ? wt : kTrivBlocks);
-    trivial_rows_kernel<<<tb, 256, 0, st>>>(q, h->d_nn, h->d_cond, h->d_trivlist, h->ntriv,
+    UParams qt = q;                      // the n0 <= 1 rows are read with the original ids
+    qt.locs = h->d_locs; qt.nuggets = d_nuggets;
+    if (h->locality && want_loglik) qt.zloc = h->d_zloc_rows;
+    trivial_rows_kernel<<<tb, 256, 0, st>>>(qt, h->d_nn, h->d_cond, h->d_trivlist, h->ntriv,
                                              want_loglik ? h->d_partials + 4 * (size_t)blocks : nullptr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -966,15 +1185,30 @@ static gpv_status read_fail_info(gpv_handle* h, int64_t* nfail, int64_t* first_f
   return GPV_OK;
 }
 
+// d_tau [cap] and d_zent [2 cap]: sized by what is allocated (a handle created without obs sees n only at the
+// first call, and a later call may bring a longer vector)
+static gpv_status ensure_tau(gpv_handle* h, int64_t n) {
+  if (n <= h->tau_cap && h->d_tau && h->d_zent) return GPV_OK;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_tau); cudaFree(h->d_zent); h->d_tau = nullptr; h->d_zent = nullptr; h->tau_cap = 0;
+  int64_t cap = (h->have_obs && h->n_obs > n) ? h->n_obs : n;
+  if (cap < 1) cap = 1;
+  CUDA_TRY(cudaMalloc(&h->d_tau, sizeof(double) * (size_t)cap));
+  CUDA_TRY(cudaMalloc(&h->d_zent, sizeof(double) * 2 * (size_t)cap));
+  h->tau_cap = cap;
+  h->nug_resident = false;
+  return GPV_OK;
+}
 static gpv_status run_zentries(gpv_handle* h, const double* nuggets_obsord, int64_t n) {
   if (n <= 0) return GPV_OK;
-  if (h->n_obs != 0 && h->have_obs && n != h->n_obs)
+  // A whole-range handle takes the nuggets of all its observations.  A row shard (gpv_create_shard / a row range)
+  // may be given the nuggets of ANY contiguous slice of the observations -- normally those located in its rows --
+  // and returns their Z entries: Zentries is elementwise (U_NZentries.cpp:110-115), so the ranks of a sharded run
+  // each upload and download only their slice instead of all n (SCALE_r01: 128 MB of replicated Z traffic per rank).
+  const bool whole = (h->nrows == h->Nlocs);
+  if (h->have_obs && h->n_obs != 0 && (whole ? n != h->n_obs : n > h->n_obs))
     return fail(GPV_ERR_ARG, "n=%lld does not match sum(obs)=%lld", (long long)n, (long long)h->n_obs);
-  if (!h->d_tau || !h->d_zent) {
-    cudaFree(h->d_tau); cudaFree(h->d_zent); h->d_tau = nullptr; h->d_zent = nullptr;
-  }
-  gpv_status s = ensure(&h->d_tau, (size_t)n); if (s) return s;
-  s = ensure(&h->d_zent, 2 * (size_t)n); if (s) return s;
+  gpv_status s = ensure_tau(h, n); if (s) return s;
   CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   zentries_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_tau, n, h->d_zent);
   g_launches++;
@@ -991,7 +1225,7 @@ extern "C" gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   CovSetup cs;
-  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, st); if (s) return s;
   int nblocks = 0;
   s = launch_sets(h, &cs, d_nuggets, d_out, packed, d_zord, skip_rows, d_loglik != nullptr, st, &nblocks);
@@ -1004,6 +1238,15 @@ extern "C" gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double
   return GPV_OK;
 }
 
+// The chunked pipeline overlaps kernel launches with device-to-host copies; that only works into page-locked
+// memory.  Into pageable memory (every R vector, plain numpy arrays) cudaMemcpyAsync blocks the host until the
+// copy is done, so the next chunk's kernel would not even be enqueued: 16 launches and no overlap.  Such
+// buffers take the single-launch path.
+static bool host_buffer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
 // shared body of gpv_u_nzentries / gpv_u_values_packed
 static gpv_status u_host_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
                                 const double* nuggets, const double* nuggets_obsord, int64_t n,
@@ -1013,14 +1256,14 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   if (n > 0 && !nuggets_obsord) return fail(GPV_ERR_ARG, "nuggets_obsord is null");
   CUDA_TRY(cudaSetDevice(h->device));
   CovSetup cs;
-  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
   h->nug_resident = false;             // d_nuggets is shared with the likelihood calls
   CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
   const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
   bool chunked = false;
-  if (h->nrows > 0 && packed && h->nchunks > 1) {
+  if (h->nrows > 0 && packed && h->nchunks > 1 && host_buffer_is_pinned(out)) {
     // overlapped pipeline: kernel of chunk c+1 (compute stream) runs while the packed values of
     // chunk c travel to the host (copy stream).  The rows of a chunk are contiguous in the packed
     // vector; the n0 <= 1 rows interleaved with them are written by the first launch.
@@ -1097,9 +1340,9 @@ static gpv_status loglik_common(gpv_handle* h, const char* covType, const double
   if (!zord && !h->z_resident) return fail(GPV_ERR_ARG, "likelihood: no data given and none resident on the handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CovSetup cs;
-  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs); if (s) return s;
+  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
-  s = ensure(&h->d_tau, (size_t)n); if (s) return s;
+  s = ensure_tau(h, n); if (s) return s;
   s = ensure(&h->d_zord, (size_t)n); if (s) return s;
   if (nuggets) {
     h->nug_resident = false;
@@ -1139,7 +1382,7 @@ extern "C" gpv_status gpv_set_scalar_nugget(gpv_handle* h, double nugget) {
   if (!h) return fail(GPV_ERR_ARG, "gpv_set_scalar_nugget: null handle");
   if (!h->have_obs) return fail(GPV_ERR_ARG, "gpv_set_scalar_nugget: handle was created without obs");
   CUDA_TRY(cudaSetDevice(h->device));
-  gpv_status s = ensure(&h->d_tau, (size_t)(h->n_obs ? h->n_obs : 1)); if (s) return s;
+  gpv_status s = ensure_tau(h, h->n_obs ? h->n_obs : 1); if (s) return s;
   const int64_t m = h->Nlocs > h->n_obs ? h->Nlocs : h->n_obs;
   fill_scalar_nugget_kernel<<<grid_for(m, 256), 256, 0, h->stream>>>(h->d_obsrank, h->Nlocs, h->n_obs, nugget, h->d_nuggets, h->d_tau);
   g_launches++;

@@ -67,7 +67,7 @@ extern "C" gpv_status gpv_multi_create(gpv_multi** out, int64_t Nlocs, int p, in
   std::vector<double> w((size_t)Nlocs + 1, 0.0);
   for (int64_t r = 0; r < Nlocs; ++r) {
     int n0 = 0;
-    for (int j = 0; j < p; ++j) n0 += revNNarray[r + (int64_t)j * Nlocs] != 0;
+    for (int j = 0; j < p; ++j) n0 += revNNarray[r + (int64_t)j * Nlocs] > 0;   // 0, NA (INT_MIN): missing
     w[r + 1] = w[r] + (double)n0 * n0 * n0;
   }
   m->cut.assign(ndev + 1, 0);

@@ -54,9 +54,6 @@ struct BandLayout {
   static constexpr int kMinBlocks = (G == 8 && NB == 3) ? GPV_BAND_MINB3 : 1;
   static constexpr int kWPB = (kMinBlocks == 1) ? 8 : 4;   // warps per block
   static constexpr int kThreads = 32 * kWPB;
-  static constexpr bool kWideTables = (kMinBlocks == 1);   // replicated exp table / shared general-nu window
-  static constexpr int kExpStride = kWideTables ? 16 : 1;
-  static constexpr int kGenWin = kWideTables ? 64 : 0;      // intervals of the general-nu table kept in shared memory
   static constexpr int kSetsPerWarp = 32 / G;
   static constexpr int kRaw = kBuf + 2 * kStage;
   // every set starts on a 128-byte line plus a skew of {0, 64, 32, 96} bytes: the row segments of the
@@ -64,6 +61,11 @@ struct BandLayout {
   // different banks
   static constexpr int kDoubles = ((kRaw + 15) / 16) * 16 + 16;
   static constexpr int kBytesPerBlock = kDoubles * 8 * kSetsPerWarp * kWPB;
+  // replicated exp table / shared general-nu window: only where the 227 KB hold them next to the sets in flight
+  // (P = 32 does not leave the room)
+  static constexpr bool kWideTables = (kMinBlocks == 1) && (kBytesPerBlock + 13312 + 1024 <= 232448);
+  static constexpr int kExpStride = kWideTables ? 16 : 1;
+  static constexpr int kGenWin = kWideTables ? 24 * (1 << GPV_TAB_SUBBITS) : 0;   // intervals of the general-nu table kept in shared memory (cov_setup.h kTabWindow)
   static_assert(G == 8 || G == 16, "lane groups of 8 or 16");
   static_assert(P > 2 * G && P <= 4 * G, "band-folded kernel: 2G < P <= 4G");
   static_assert(G == 8 || NB == 3, "four bands of 16 lanes do not fit the register file");
@@ -134,7 +136,7 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
 #pragma unroll
       for (int b = 0; b < NB; ++b) sp |= cov_general_special(r2[b], q.tab, &idx[b]);
       if constexpr (GW > 0) {
-        const int win0 = q.tab.nint - GW;
+        const int win0 = q.tab.win0;
 #pragma unroll
         for (int b = 0; b < NB; ++b) { idx[b] -= win0; outside |= (unsigned)idx[b] >= (unsigned)GW; }
       }
@@ -146,7 +148,7 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
         for (int b = 0; b < NB; ++b) v[b] = cov_general_fast_shared<(GW > 0 ? GW : 1)>(r2[b], gtab + idx[b]);
       } else {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast(r2[b], idx[b] + (GW > 0 ? q.tab.nint - GW : 0), q.tab);
+        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast(r2[b], idx[b] + (GW > 0 ? q.tab.win0 : 0), q.tab);
       }
     } else {
       cov_eval_n<KIND, NB, C, ES>(r2, v, q, etab);
@@ -216,15 +218,16 @@ u_band_kernel(const UParams q) {
   build_store_table_band<G, P, D>(stab);
   for (int i = threadIdx.x; i < 64 * ES; i += blockDim.x) etab_s[i] = kExp2Tab[i / ES];
   const double* etab = etab_s + (ES > 1 ? (lane & (ES - 1)) : 0);
-  // general nu: the top kGenWin intervals of the coefficient table (w from w_max 2^-32 up) in shared memory,
-  // coefficient-major like the global table; pairs outside it take the global-memory path
+  // general nu: a window of kGenWin intervals of the coefficient table (24 octaves of w, placed by the host where
+  // the handle's neighbour distances are: CovTable::win0) in shared memory, coefficient-major like the global
+  // table; pairs outside it take the global-memory path
   constexpr int GW = GENERAL ? LY::kGenWin : 0;
   __shared__ double gtab[(GW > 0) ? (kTabDeg + 1) * GW : 1];
   if constexpr (GW > 0) {
-    const int win0 = q.tab.nint - GW;
+    const int win0 = q.tab.win0;
     for (int i = threadIdx.x; i < (kTabDeg + 1) * GW; i += blockDim.x) {
       const int k = i / GW, j = i % GW + win0;
-      gtab[i] = (j >= 0) ? q.tab.coef[tab_coef_index(k, j)] : 0.0;
+      gtab[i] = (j < q.tab.nint) ? q.tab.coef[tab_coef_index(k, j)] : 0.0;
     }
   }
   __syncthreads();

@@ -45,6 +45,7 @@ struct CovTable {
   int sub_bits;
   int deg;
   double w_split;       // w >= w_split : table holds exp(+s) * cov, multiply by exp(-s)
+  int win0;             // first interval of the window the band kernels keep in shared memory (u_band.cuh)
   double nu, xmu, gam1, gam2, gampl, gammi, normcon;   // direct (out-of-table) evaluator
   int nl;
 };

@@ -103,19 +103,47 @@ static void handle_finalizer(SEXP ptr) {
   gpv_handle* h = (gpv_handle*)R_ExternalPtrAddr(ptr);
   if (h) { gpv_destroy(h); R_ClearExternalPtr(ptr); }
 }
+static void multi_finalizer(SEXP ptr) {
+  gpv_multi* m = (gpv_multi*)R_ExternalPtrAddr(ptr);
+  if (m) { gpv_multi_destroy(m); R_ClearExternalPtr(ptr); }
+}
+static int is_multi(SEXP ptr) { return R_ExternalPtrTag(ptr) == Rf_install("gpv_multi"); }
+static gpv_multi* get_multi(SEXP ptr) {
+  gpv_multi* m = (gpv_multi*)R_ExternalPtrAddr(ptr);
+  if (!m) Rf_error("gpvecchia_b200: stale device handle (vecchia.approx was deserialised?); re-create it");
+  return m;
+}
 
 SEXP gpvb200_create(SEXP locsord, SEXP revNNarray, SEXP revCond, SEXP obs) {
   const int64_t N = Rf_nrows(locsord);
   const int d = Rf_ncols(locsord), p = Rf_ncols(revNNarray);
+  /* Rf_coerceVector returns its ARGUMENT when the type already matches (the usual case: GpGp / FNN neighbour
+   * arrays are integer), so nothing may be written through `nn`: is.na(vecchia.approx$U.prep$revNNarray) is
+   * still needed by the reference's R code after this call (createU.R:17-18, 90-91, 158).  The library reads
+   * NA_integer_ (INT_MIN), like 0, as "missing" (prep_nn_kernel), so createU.R:146-147 needs no copy here. */
   SEXP nn = PROTECT(Rf_coerceVector(revNNarray, INTSXP));
-  int* ip = INTEGER(nn);
-  for (R_xlen_t i = 0; i < XLENGTH(nn); ++i) if (ip[i] == NA_INTEGER) ip[i] = 0;   /* createU.R:146-147 */
+  const int* ip = INTEGER(nn);
   SEXP ob = PROTECT(Rf_coerceVector(obs, LGLSXP));
-  gpv_handle* h = NULL;
-  check(gpv_create(&h, N, p, d, REAL(locsord), ip, LOGICAL(revCond), GPV_COND_RLOGICAL_I32,
-                   LOGICAL(ob), 0, N, device_from_option()));
-  SEXP ptr = PROTECT(R_MakeExternalPtr(h, Rf_install("gpv_handle"), R_NilValue));
-  R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  SEXP devs = Rf_GetOption1(Rf_install("GPvecchia.b200.devices"));   /* e.g. options(GPvecchia.b200.devices = 0:7) */
+  SEXP ptr;
+  if (devs != R_NilValue && XLENGTH(devs) > 1) {
+    /* one R process, several GPUs: rows split into contiguous ranges, one worker thread per device inside the
+     * library (gpv_multi_*); the handle is tagged so the calls below dispatch on it */
+    SEXP di = PROTECT(Rf_coerceVector(devs, INTSXP));
+    gpv_multi* m = NULL;
+    gpv_status st = gpv_multi_create(&m, N, p, d, REAL(locsord), ip, LOGICAL(revCond), GPV_COND_RLOGICAL_I32,
+                                     LOGICAL(ob), INTEGER(di), (int)XLENGTH(di));
+    UNPROTECT(1);
+    check(st);
+    ptr = PROTECT(R_MakeExternalPtr(m, Rf_install("gpv_multi"), R_NilValue));
+    R_RegisterCFinalizerEx(ptr, multi_finalizer, TRUE);
+  } else {
+    gpv_handle* h = NULL;
+    check(gpv_create(&h, N, p, d, REAL(locsord), ip, LOGICAL(revCond), GPV_COND_RLOGICAL_I32,
+                     LOGICAL(ob), 0, N, devs != R_NilValue ? Rf_asInteger(devs) : device_from_option()));
+    ptr = PROTECT(R_MakeExternalPtr(h, Rf_install("gpv_handle"), R_NilValue));
+    R_RegisterCFinalizerEx(ptr, handle_finalizer, TRUE);
+  }
   double nobs = 0;                                            /* for likelihood calls that pass zord = NULL */
   for (R_xlen_t i = 0; i < XLENGTH(ob); ++i) nobs += (LOGICAL(ob)[i] == TRUE);
   Rf_setAttrib(ptr, Rf_install("n_obs"), Rf_ScalarReal(nobs));
@@ -130,18 +158,24 @@ static gpv_handle* get_handle(SEXP ptr) {
 }
 
 SEXP gpvb200_set_revcond(SEXP ptr, SEXP revCond) {
-  check(gpv_set_revcond(get_handle(ptr), LOGICAL(revCond), GPV_COND_RLOGICAL_I32));
+  if (is_multi(ptr)) check(gpv_multi_set_revcond(get_multi(ptr), LOGICAL(revCond), GPV_COND_RLOGICAL_I32));
+  else check(gpv_set_revcond(get_handle(ptr), LOGICAL(revCond), GPV_COND_RLOGICAL_I32));
   return R_NilValue;
 }
 
 /* allLentries of createU.R:158-160 (packed U values followed by Zentries), straight from the GPU */
 SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
-  gpv_handle* h = get_handle(ptr);
   const int64_t n = XLENGTH(nuggets_ord);
-  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(gpv_packed_len(h) + 2 * n)));
+  const int multi = is_multi(ptr);
+  const int64_t len = multi ? gpv_multi_packed_len(get_multi(ptr)) : gpv_packed_len(get_handle(ptr));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(len + 2 * n)));
   int64_t nfail = 0, first = -1;
-  check(gpv_u_values_packed(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                            REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first));
+  gpv_status st = multi
+      ? gpv_multi_u_values_packed(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                                  REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first)
+      : gpv_u_values_packed(get_handle(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                            REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first);
+  if (st != GPV_OK) { UNPROTECT(1); check(st); }
   warn_fail(nfail, first);
   UNPROTECT(1);
   return out;
@@ -149,12 +183,14 @@ SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_or
 
 /* dgCMatrix slots of U: list(p, i, size) once per vecchia.approx ... */
 SEXP gpvb200_csc_pattern(SEXP ptr) {
-  gpv_handle* h = get_handle(ptr);
+  const int multi = is_multi(ptr);
   int64_t ncols = 0, nnz = 0, size = 0;
-  check(gpv_csc_dims(h, &ncols, &nnz, &size));
+  check(multi ? gpv_multi_csc_dims(get_multi(ptr), &ncols, &nnz, &size) : gpv_csc_dims(get_handle(ptr), &ncols, &nnz, &size));
   SEXP p = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)(ncols + 1)));
   SEXP i = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
-  check(gpv_u_csc_pattern(h, INTEGER(p), INTEGER(i)));
+  gpv_status st = multi ? gpv_multi_u_csc_pattern(get_multi(ptr), INTEGER(p), INTEGER(i))
+                        : gpv_u_csc_pattern(get_handle(ptr), INTEGER(p), INTEGER(i));
+  if (st != GPV_OK) { UNPROTECT(2); check(st); }
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
   SET_VECTOR_ELT(out, 0, p);
   SET_VECTOR_ELT(out, 1, i);
@@ -164,18 +200,23 @@ SEXP gpvb200_csc_pattern(SEXP ptr) {
 }
 /* ... and @x per createU call: kernel + createU.R:158-160 + the triplet sort of sparseMatrix (:161) */
 SEXP gpvb200_U_values_csc(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
-  gpv_handle* h = get_handle(ptr);
+  const int multi = is_multi(ptr);
   int64_t nnz = 0, nfail = 0, first = -1;
-  check(gpv_csc_dims(h, NULL, &nnz, NULL));
+  check(multi ? gpv_multi_csc_dims(get_multi(ptr), NULL, &nnz, NULL) : gpv_csc_dims(get_handle(ptr), NULL, &nnz, NULL));
   SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
-  check(gpv_u_values_csc(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                         REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first));
+  gpv_status st = multi
+      ? gpv_multi_u_values_csc(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                               REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first)
+      : gpv_u_values_csc(get_handle(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                         REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first);
+  if (st != GPV_OK) { UNPROTECT(1); check(st); }
   warn_fail(nfail, first);
   UNPROTECT(1);
   return out;
 }
 /* list(colindices, rowpointers) of R/U_sparsity.R:36-73 */
 SEXP gpvb200_U_sparsity(SEXP ptr) {
+  if (is_multi(ptr)) Rf_error("U_sparsity arrays: use a single-device handle (or the compressed-column pattern)");
   gpv_handle* h = get_handle(ptr);
   int64_t nnz = 0;
   check(gpv_csc_dims(h, NULL, &nnz, NULL));
@@ -191,6 +232,7 @@ SEXP gpvb200_U_sparsity(SEXP ptr) {
 
 /* scalar nugget built on the device; afterwards the likelihood calls may pass NULL (R: NULL) vectors */
 SEXP gpvb200_set_scalar_nugget(SEXP ptr, SEXP nugget) {
+  if (is_multi(ptr)) Rf_error("resident scalar nugget: single-device handle only");
   check(gpv_set_scalar_nugget(get_handle(ptr), Rf_asReal(nugget)));
   return R_NilValue;
 }
@@ -198,8 +240,17 @@ SEXP gpvb200_set_scalar_nugget(SEXP ptr, SEXP nugget) {
 /* c(quadform.num, logdet.num, nfail) of vecchia_likelihood.R:74-76, no U materialisation */
 SEXP gpvb200_loglik_numerator(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord,
                               SEXP nuggets_ord, SEXP zord, SEXP skip_rows) {
-  gpv_handle* h = get_handle(ptr);
   SEXP out = PROTECT(Rf_allocVector(REALSXP, 3));
+  if (is_multi(ptr)) {
+    if (Rf_isNull(nuggets_all_ord) || Rf_isNull(nuggets_ord) || Rf_isNull(zord)) { UNPROTECT(1); Rf_error("the multi-device handle takes all three vectors"); }
+    gpv_status st = gpv_multi_loglik_numerator(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                                               REAL(nuggets_all_ord), REAL(nuggets_ord), REAL(zord), XLENGTH(zord),
+                                               (int64_t)Rf_asReal(skip_rows), REAL(out));
+    UNPROTECT(1);
+    check(st);
+    return out;
+  }
+  gpv_handle* h = get_handle(ptr);
   check(gpv_loglik_numerator(h, CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
                              Rf_isNull(nuggets_all_ord) ? NULL : REAL(nuggets_all_ord),
                              Rf_isNull(nuggets_ord) ? NULL : REAL(nuggets_ord), Rf_isNull(zord) ? NULL : REAL(zord),
@@ -209,10 +260,41 @@ SEXP gpvb200_loglik_numerator(SEXP ptr, SEXP covType, SEXP covparms, SEXP nugget
   return out;
 }
 
-SEXP gpvb200_MaternFun(SEXP distmat, SEXP covparms) {
-  SEXP out = PROTECT(Rf_duplicate(distmat));
-  check(gpv_MaternFun(REAL(distmat), XLENGTH(distmat), REAL(covparms), REAL(out), device_from_option()));
+/* c(loglik, quadform.num, logdet.num, quadform.denom, logdet.denom, nfail): the whole vecchia_likelihood for
+ * cond.yz = 'z' (every neighbour conditioned on the response: U_y U_y^T is diagonal, so the denominator of
+ * vecchia_likelihood.R:85-91 is a per-row closed form); other layouts return an error and R falls back to U2V */
+SEXP gpvb200_loglik_z(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord, SEXP zord) {
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 6));
+  gpv_status st;
+  if (is_multi(ptr))
+    st = gpv_multi_loglik_z(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                            REAL(nuggets_all_ord), REAL(nuggets_ord), REAL(zord), XLENGTH(zord), REAL(out));
+  else
+    st = gpv_loglik_z(get_handle(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
+                      Rf_isNull(nuggets_all_ord) ? NULL : REAL(nuggets_all_ord),
+                      Rf_isNull(nuggets_ord) ? NULL : REAL(nuggets_ord), Rf_isNull(zord) ? NULL : REAL(zord),
+                      Rf_isNull(zord) ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(zord), -1, REAL(out));
   UNPROTECT(1);
+  check(st);
+  return out;
+}
+
+/* MaternFun(distmat, covparms) / EsqeFun(distmat, covparms): the reference exports MaternFun to users
+ * (NAMESPACE:3) and has a .Call wrapper for EsqeFun (R/RcppExports.R:4-10); same names, same shapes */
+SEXP gpvb200_MaternFun(SEXP distmat, SEXP covparms) {
+  if (!Rf_isReal(distmat) || !Rf_isReal(covparms) || XLENGTH(covparms) < 3) Rf_error("MaternFun(distmat, c(sig2, range, smooth))");
+  SEXP out = PROTECT(Rf_duplicate(distmat));                 /* keeps dim */
+  gpv_status st = gpv_MaternFun(REAL(distmat), XLENGTH(distmat), REAL(covparms), REAL(out), device_from_option());
+  UNPROTECT(1);
+  check(st);
+  return out;
+}
+SEXP gpvb200_EsqeFun(SEXP distmat, SEXP covparms) {
+  if (!Rf_isReal(distmat) || !Rf_isReal(covparms) || XLENGTH(covparms) < 4) Rf_error("EsqeFun(distmat, c(sig2_1, r1, sig2_2, r2))");
+  SEXP out = PROTECT(Rf_duplicate(distmat));
+  gpv_status st = gpv_EsqeFun(REAL(distmat), XLENGTH(distmat), REAL(covparms), REAL(out), device_from_option());
+  UNPROTECT(1);
+  check(st);
   return out;
 }
 
@@ -262,7 +344,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_b200_U_sparsity", (DL_FUNC)&gpvb200_U_sparsity, 1},
     {"_GPvecchia_b200_set_scalar_nugget", (DL_FUNC)&gpvb200_set_scalar_nugget, 2},
     {"_GPvecchia_b200_loglik_numerator", (DL_FUNC)&gpvb200_loglik_numerator, 7},
-    {"_GPvecchia_b200_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},
+    {"_GPvecchia_b200_loglik_z", (DL_FUNC)&gpvb200_loglik_z, 6},
+    {"_GPvecchia_MaternFun", (DL_FUNC)&gpvb200_MaternFun, 2},      /* src/RcppExports.cpp:156-157: same names, arity 2 */
+    {"_GPvecchia_EsqeFun", (DL_FUNC)&gpvb200_EsqeFun, 2},
     {"_GPvecchia_ic0", (DL_FUNC)&gpvb200_ic0, 3},                   /* src/RcppExports.cpp: same names and arities */
     {"_GPvecchia_createUcppM", (DL_FUNC)&gpvb200_createUcppM, 3},
     {"_GPvecchia_createUcpp", (DL_FUNC)&gpvb200_createUcpp, 4},

@@ -55,6 +55,7 @@ void Rf_warning(const char*, ...);
 typedef void (*R_CFinalizer_t)(SEXP);
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
+SEXP R_ExternalPtrTag(SEXP);
 void R_ClearExternalPtr(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 #endif

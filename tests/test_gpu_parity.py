@@ -794,3 +794,50 @@ def test_single_process_multi_device_front_end(layout):
             if layout == "zy" and len(devices) == 3:
                 # the n dummy rows are free: the first cut lies beyond them
                 assert mh.row_cuts[1] > n
+
+
+@pytest.mark.parametrize("layout", ["z", "zy", "SGV"])
+def test_locality_layer_changes_the_order_of_work_not_the_results(layout, monkeypatch):
+    """Large handles keep a Morton-sorted replica of the per-location data and process the rows of every output
+    chunk in Morton order (gpv_capi.cu, locality layer; automatic above ~2e6 locations).  GPV_LOCALITY=1 forces it
+    on a small problem: U values (row-major, packed, chunked pipeline, compressed-column), failure reporting and
+    the likelihood sums must equal the plain path -- values bit for bit, sums to reduction-order rounding."""
+    n, m = 70000, 12                    # >= 65536 sets: the chunked packed pipeline is active
+    locs = H.make_locs(n, 2, stream=131)
+    z = H.make_data(n, stream=131)
+    if layout == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        nug_all = np.concatenate([H.make_nuggets(n, stream=131), np.zeros(n)])
+        skip = n
+    else:
+        locs2, NN = locs, H.ordered_nn_kdtree(locs, m)
+        Cond = H.layout_yz(NN, "z") if layout == "z" else H.whichCondOnLatent(NN)
+        obs = np.ones(n, dtype=bool)
+        nug_all = H.make_nuggets(n, stream=131)
+        skip = 0
+    nug_all[1234] = -30.0               # a few failing rows: nfail / first_fail must agree as well
+    revNN, revCond = H.rev(NN), H.rev(Cond)
+    tau = np.abs(nug_all[:n])
+    res = {}
+    for loc in ("0", "1"):
+        monkeypatch.setenv("GPV_LOCALITY", loc)
+        out = {}
+        for covType, cp in (("matern", [1.0, H.default_range(n, 2), 1.5]), ("matern", [1.0, H.default_range(n, 2), 0.8])):
+            with G.UHandle(locs2, revNN, revCond, obs=obs) as h:
+                r = h.U_NZentries(covType, cp, nug_all, tau)
+                packed, nf, ff = h.values_packed(covType, cp, nug_all, tau)
+                ll = h.loglik_numerator(covType, cp, nug_all, tau, z, skip_rows=skip)
+                try:
+                    csc = h.values_csc(covType, cp, nug_all, tau)[0]
+                except G.GpvError:          # layouts whose sets hold a U row twice go the triplet route
+                    csc = None
+            out[cp[2]] = (r["Lentries"], r["nfail"], r["first_fail"], packed, nf, ff, ll, csc)
+        res[loc] = out
+    for nu in res["0"]:
+        a, b = res["0"][nu], res["1"][nu]
+        assert a[1] == b[1] > 0 and a[2] == b[2] and a[4] == b[4] and a[5] == b[5]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+        if a[7] is not None:
+            assert b[7] is not None and np.array_equal(a[7], b[7])
+        assert np.allclose(np.asarray(a[6][:2], dtype=float), np.asarray(b[6][:2], dtype=float), rtol=1e-12, atol=0)
+        assert a[6][2] == b[6][2]
