@@ -413,20 +413,30 @@ __global__ void obs_terms_kernel(const double* __restrict__ zord, const double* 
 // out[0] = quadform.num, out[1] = logdet.num, out[2] = nfail, out[3] = quadform.denom,
 // out[4] = logdet.denom (the last two only for pure `z` layouts), all restricted to the shard.
 // Single thread, fixed order: run-to-run reproducible.
+// One warp, fixed order: lane l adds the partials l, l + 32, ... in that order, then a butterfly over the lanes.
+// The order depends on nothing but the number of blocks: run-to-run reproducible, like the serial sum it replaces
+// (which took 40 us for 600 partials on one thread).
 __global__ void finalize_loglik_kernel(const double* __restrict__ row_partials, int nrow_blocks,
                                        const double* __restrict__ obs_partials, int nobs_blocks,
                                        const unsigned long long* __restrict__ nfail,
                                        double* __restrict__ out, int nout) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double q = 0.0, l = 0.0, qd = 0.0, ld = 0.0;
-  for (int i = 0; i < nrow_blocks; ++i) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  double q = 0.0, l = 0.0, qd = 0.0, ld = 0.0, qo = 0.0, lo = 0.0;
+  for (int i = lane; i < nrow_blocks; i += 32) {
     q += row_partials[4 * i]; l += row_partials[4 * i + 1];
     qd += row_partials[4 * i + 2]; ld += row_partials[4 * i + 3];
   }
+  if (obs_partials != nullptr)
+    for (int i = lane; i < nobs_blocks; i += 32) { qo += obs_partials[2 * i]; lo += obs_partials[2 * i + 1]; }
+  for (int o = 16; o >= 1; o >>= 1) {
+    q += __shfl_xor_sync(0xffffffffu, q, o); l += __shfl_xor_sync(0xffffffffu, l, o);
+    qd += __shfl_xor_sync(0xffffffffu, qd, o); ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    qo += __shfl_xor_sync(0xffffffffu, qo, o); lo += __shfl_xor_sync(0xffffffffu, lo, o);
+  }
+  if (lane != 0) return;
   double logdet = -2.0 * l;
   if (obs_partials != nullptr) {
-    double qo = 0.0, lo = 0.0;
-    for (int i = 0; i < nobs_blocks; ++i) { qo += obs_partials[2 * i]; lo += obs_partials[2 * i + 1]; }
     q += qo;
     logdet += lo;   // -2 * sum log(1/sqrt(tau)) = + sum log tau
   }

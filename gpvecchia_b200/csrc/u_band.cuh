@@ -21,13 +21,12 @@
 
 namespace gpv {
 
-#ifndef GPV_BAND_PAIR_UNROLL
-#define GPV_BAND_PAIR_UNROLL 1
+#ifndef GPV_BAND_STAGGER
+#define GPV_BAND_STAGGER 6000   // cycles; measured: esqe 2.68 -> 2.58 ms, the Matern forms unchanged (profiles/r02_variants.log)
 #endif
 #ifndef GPV_BAND_MINB3
 #define GPV_BAND_MINB3 3
 #endif
-constexpr int kBandPairUnroll = GPV_BAND_PAIR_UNROLL;   // pair-stage iterations per loop trip
 template <int G, int P, int D>
 struct BandLayout {
   static constexpr int NB = (P + G - 1) / G;               // bands: 3 or 4
@@ -36,6 +35,9 @@ struct BandLayout {
   static constexpr int kScratch = tri_col(P, P);           // per-lane dump slots for inactive pair stores
   static constexpr int kBuf = ((tri_col(P, P) + G + 1) / 2) * 2;
   static constexpr int kT = P / 2;                         // pair-stage iterations
+  // pair-stage iterations per loop trip: 2 for the 16-lane groups (three chains per iteration; measured 6.46 ->
+  // 6.15 ms at m = 40, d = 3), 1 for the 8-lane groups (four chains; unrolling costs 1 %): profiles/r02_variants.log
+  static constexpr int kPairUnroll = (G == 16) ? 2 : 1;
   static constexpr int PX = NB * G;                        // coordinate row stride (>= P, even)
   static constexpr int kX = DD * PX;
   static constexpr int kNug = PX;
@@ -122,7 +124,8 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
   const uint4* stab_lane = stab + gl;
   char* Asb = reinterpret_cast<char*>(As);
   const double guard = (KIND == COV_GENERAL) ? 0.0 : kMathC[7];
-#pragma unroll kBandPairUnroll
+  constexpr int UNR = (KIND == COV_GENERAL) ? 1 : LY::kPairUnroll;   // the general branch spills when unrolled
+#pragma unroll UNR
   for (int t = 1; t <= LY::kT; ++t) {
     const uint4 offs = stab_lane[(t - 1) * G];
     const int jp[4] = {(int)(offs.z & 0xffffu), (int)(offs.z >> 16), (int)(offs.w & 0xffffu), (int)(offs.w >> 16)};
@@ -323,6 +326,15 @@ u_band_kernel(const UParams q) {
     return n0;
   };
 
+#if GPV_BAND_STAGGER > 0 && !defined(GPV_SIMT_EMU)
+  // the two warps of a scheduler (w and w + kWPB/2) would otherwise run their phases in lock step -- both in the
+  // fp64-bound pair stage, then both in the shared-memory-bound factorisation; start the second one half a batch
+  // later so that the phases interleave (identical work per batch: the offset persists)
+  if (LY::kWPB == 8 && warp >= LY::kWPB / 2) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < GPV_BAND_STAGGER) {}
+  }
+#endif
   int bsel = 0;
   fetch_raw(first + sub, stage0);
   __pipeline_commit();
@@ -374,7 +386,6 @@ u_band_kernel(const UParams q) {
     }
 
     // ---- 3. covariance pairs -> shared staging (packed lower triangle) -------------------------------
-#if !GPV_HACK_NOPAIR   /* GPV_HACK_*: timing experiments only (wrong values), never set in the product build */
     if (GENERAL) {
       pair_stage_band<COV_GENERAL, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d);
     } else {
@@ -385,7 +396,6 @@ u_band_kernel(const UParams q) {
         default: pair_stage_band<COV_ESQE, G, P, D>(q, buf, xs, x, gl, stab, etab, gtab, d); break;
       }
     }
-#endif
     if (__any_sync(FULL, npad > 0)) {
       // padding occupies the leading indices: zero columns 0..npad-1 of the staged triangle
       __syncwarp();

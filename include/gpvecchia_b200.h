@@ -81,7 +81,14 @@ gpv_status gpv_set_revcond(gpv_handle* h, const void* revCondOnLatent, gpv_cond_
 
 /* ---- U_NZentries through a handle (host buffers) --------------------------------------------
  * nuggets[Nlocs] (nuggets.all.ord), nuggets_obsord[n].  Lentries: column-major (row_end-
- * row_begin) x p, zero-filled beyond n0 like the reference; Zentries[2n] or NULL. */
+ * row_begin) x p, zero-filled beyond n0 like the reference; Zentries[2n] or NULL.
+ * A whole-range handle takes the nuggets of all its observations (n = sum(obs)).  A row shard may be given
+ * the nuggets of any contiguous slice of the observations (n <= sum(obs)) and returns THEIR Zentries
+ * (elementwise, U_NZentries.cpp:110-115): the ranks of a sharded run each move only their slice.
+ * revNNarray ids: 1-based; 0, NA_integer_ and any non-positive value are "missing"; an id > Nlocs makes
+ * gpv_create fail with GPV_ERR_ARG.
+ * Host output buffers: page-locked memory gets the overlapped (chunked) copy pipeline, pageable memory one
+ * launch and one copy. */
 gpv_status gpv_u_nzentries(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
                            const double* nuggets, const double* nuggets_obsord, int64_t n,
                            double* Lentries, double* Zentries, int64_t* nfail, int64_t* first_fail);
