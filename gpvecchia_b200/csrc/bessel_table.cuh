@@ -242,25 +242,28 @@ __device__ __forceinline__ double cov_general_fast(double r2, int idx, const Cov
   for (int k = kTabDeg - 1; k >= 0; --k) acc = fma(acc, v, __ldg(cf + k * kTabStride));
   return acc;
 }
-// The same polynomial with the coefficients read from the shared-memory window of the table (u_band.cuh):
-// `cf` points at interval j of a coefficient-major array with GW intervals per row.  Measured: 2.2 wavefronts per
-// gather (two half-warps), against 2.4 from global memory through a 29 KB L1 -- the gain of the window is
-// that it cannot be evicted by the streams (profiles/r02b_u_band_general_*).
+// The same polynomial with the coefficients read from the shared-memory window of the table (u_band.cuh).  The
+// window is stored as two 32-bit planes (high words, low words), coefficient-major with GW intervals per row, and a
+// coefficient is two LDS.32: a warp's lanes sit on a few dozen neighbouring intervals, i.e. on DIFFERENT 4-byte
+// banks (32 of them), one wavefront per load.  As 8-byte words the same gather hits the birthday problem of 16 lanes
+// on 16 bank pairs: measured 3.0 wavefronts per LDS.64 (profiles/r02_u_band_general_*), 2.4 from global memory.
 template <int GW>
-__device__ __forceinline__ double cov_general_fast_shared(double r2, const double* __restrict__ cf) {
+__device__ __forceinline__ double cov_general_fast_shared(double r2, const unsigned* __restrict__ hi_w,
+                                                          const unsigned* __restrict__ lo_w) {
   const int hi = __double2hiint(r2), lo = __double2loint(r2);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const int keep = 0x000fffff & ~((1 << (20 - kTabSubBits)) - 1);
   const double mc = __hiloint2double((hi & keep) | (1 << (19 - kTabSubBits)) | 0x3ff00000, 0);
   const double v = m - mc;
+  auto cf = [&](int k) { return __hiloint2double((int)hi_w[k * GW], (int)lo_w[k * GW]); };
   // even / odd halves in u = v^2: two independent Horner chains instead of one of deg + 1 terms
   constexpr int KE = (kTabDeg / 2) * 2, KO = ((kTabDeg - 1) / 2) * 2 + 1;   // highest even / odd power
   const double u = v * v;
-  double ev = cf[KE * GW], od = cf[KO * GW];
+  double ev = cf(KE), od = cf(KO);
 #pragma unroll
-  for (int k = KE - 2; k >= 0; k -= 2) ev = fma(ev, u, cf[k * GW]);
+  for (int k = KE - 2; k >= 0; k -= 2) ev = fma(ev, u, cf(k));
 #pragma unroll
-  for (int k = KO - 2; k >= 1; k -= 2) od = fma(od, u, cf[k * GW]);
+  for (int k = KO - 2; k >= 1; k -= 2) od = fma(od, u, cf(k));
   return fma(od, v, ev);
 }
 // Slow path (per lane correct for anything): zero distance, far pairs (exp split), arguments outside

@@ -116,7 +116,7 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
                                                      const double (&x)[BandLayout<G, P, D>::NB][BandLayout<G, P, D>::DD],
                                                      int gl, const uint4* __restrict__ stab,
                                                      const double* __restrict__ etab,
-                                                     const double* __restrict__ gtab, int d) {
+                                                     const unsigned* __restrict__ gtab, int d) {
   using LY = BandLayout<G, P, D>;
   constexpr int NB = LY::NB;
   constexpr int ES = (KIND == COV_GENERAL) ? 1 : LY::kExpStride;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void pair_stage_band_impl(const C& q, double* __restr
         for (int b = 0; b < NB; ++b) v[b] = cov_general_slow(r2[b], q, etab);
       } else if (GW > 0 && !__any_sync(0xffffffffu, outside)) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast_shared<(GW > 0 ? GW : 1)>(r2[b], gtab + idx[b]);
+        for (int b = 0; b < NB; ++b) v[b] = cov_general_fast_shared<(GW > 0 ? GW : 1)>(r2[b], gtab + idx[b], gtab + (kTabDeg + 1) * GW + idx[b]);
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) v[b] = cov_general_fast(r2[b], idx[b] + (GW > 0 ? q.tab.win0 : 0), q.tab);
@@ -178,7 +178,7 @@ __device__ __forceinline__ void pair_stage_band(const UParams& q, double* __rest
                                                 const double (&x)[BandLayout<G, P, D>::NB][BandLayout<G, P, D>::DD],
                                                 int gl, const uint4* __restrict__ stab,
                                                 const double* __restrict__ etab,
-                                                const double* __restrict__ gtab, int d) {
+                                                const unsigned* __restrict__ gtab, int d) {
   if constexpr (KIND != COV_GENERAL) {
     const CovConsts cc = {q.c0, q.c1, q.c2, q.c3, q.c4};
     pair_stage_band_fn<KIND, G, P, D>(cc, As, xs, x, gl, stab, etab, d);
@@ -225,12 +225,15 @@ u_band_kernel(const UParams q) {
   // the handle's neighbour distances are: CovTable::win0) in shared memory, coefficient-major like the global
   // table; pairs outside it take the global-memory path
   constexpr int GW = GENERAL ? LY::kGenWin : 0;
-  __shared__ double gtab[(GW > 0) ? (kTabDeg + 1) * GW : 1];
+  // stored as a plane of high words followed by a plane of low words (bessel_table.cuh: cov_general_fast_shared)
+  __shared__ unsigned gtab[(GW > 0) ? 2 * (kTabDeg + 1) * GW : 1];
   if constexpr (GW > 0) {
     const int win0 = q.tab.win0;
     for (int i = threadIdx.x; i < (kTabDeg + 1) * GW; i += blockDim.x) {
       const int k = i / GW, j = i % GW + win0;
-      gtab[i] = (j < q.tab.nint) ? q.tab.coef[tab_coef_index(k, j)] : 0.0;
+      const double c = (j < q.tab.nint) ? q.tab.coef[tab_coef_index(k, j)] : 0.0;
+      gtab[i] = (unsigned)__double2hiint(c);
+      gtab[(kTabDeg + 1) * GW + i] = (unsigned)__double2loint(c);
     }
   }
   __syncthreads();

@@ -780,7 +780,7 @@ def test_single_process_multi_device_front_end(layout):
     # the oracle's answer in the packed (createU.R:158-160) order: every device list below -- all GPUs of the box
     # among them -- is held to the ORACLE, not only to the one-GPU output
     ref = O.U_NZentries(O.max_threads(), n, locs2, revNN, _rc_double(revCond), nug_all, tau, "matern", np.array(cp))
-    keep = (revNN != 0).ravel()
+    keep = (revNN[:, ::-1] != 0).ravel()       # Lentries holds a row's n0 values in its FIRST n0 slots
     ref_packed = np.concatenate([ref["Lentries"].ravel()[keep], ref["Zentries"]])
     ref_scale = np.concatenate([np.repeat(np.abs(ref["Lentries"]).max(axis=1), revNN.shape[1])[keep], np.abs(ref["Zentries"])])
     if layout == "zy":
