@@ -285,7 +285,7 @@ def time_reference(S, wl, n_total, threads, target_s, backends=("openblas", "tex
     """(sets/s, backend, k, passes, seconds) of the compiled reference on about target_s seconds of CPU work: a pilot
     picks the faster of LAPACK (OpenBLAS from scipy) and the published unblocked chol / back substitution."""
     from oracle import ref_native as RN
-    k0 = 4000
+    k0 = min(4000, n_total)
     pr, nfull = reference_prefix_problem(S, wl, n_total, k0)
     rates = {}
     for b in backends:
@@ -296,7 +296,7 @@ def time_reference(S, wl, n_total, threads, target_s, backends=("openblas", "tex
         rates[b] = nfull / (time.perf_counter() - t0)
     best = max(rates, key=rates.get)
     RN.force_textbook(best == "textbook")
-    k = int(min(200_000, max(k0, rates[best] * min(target_s, 4.0))))
+    k = int(min(n_total, 200_000, max(k0, rates[best] * min(target_s, 4.0))))
     pr, nfull = reference_prefix_problem(S, wl, n_total, k)
     pr.run(threads)                                      # page-fault / thread-pool warm-up
     passes = max(1, int(round(target_s / max(nfull / rates[best], 1e-3))))
@@ -381,7 +381,7 @@ def reference_arm(args, name, wl, n_total, world, north):
         from oracle import ref_native as RN
         rate0, backend, _, _, _, rates = time_reference(S, wl, n_total, threads, target_s=1.5)
         RN.force_textbook(backend == "textbook")
-        k = int(min(200_000, max(4000, rate0 * 3.0)))        # ~3 s of CPU work per step
+        k = int(min(n_total, 200_000, max(4000, rate0 * 3.0)))        # ~3 s of CPU work per step
         pr, nfull = reference_prefix_problem(S, wl, n_total, k)
         run = lambda: pr.run(threads)                        # noqa: E731
         kind = "reference"
@@ -390,7 +390,7 @@ def reference_arm(args, name, wl, n_total, world, north):
                   f"{threads} OpenMP threads, chol/solve backend {backend}")
     else:
         import oracle as O
-        k = 60_000
+        k = min(60_000, n_total)
         locs = S.make_locs(n_total, wl["d"], stream=2)[:k]
         tau = S.make_nuggets(n_total, stream=2)[:k]
         revNN = S.rev(S.ordered_nn_kdtree(locs, wl["m"])).astype(np.int32)
@@ -518,7 +518,7 @@ class Runner:
         pr = O.RowsProblem(pb["locs"], pb["revNN"][rows], pb["revCond"][rows], 0, pb["nug_all"], self.wl["covType"],
                            pb["covparms"])
         pr.run(host_threads())
-        ref = pr.Lentries()
+        ref = pr.Lentries().copy()
         err = float((np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max())
         # structural pattern: n0 values, then exact zeros (U_NZentries.cpp:33,63).  (Not `got == 0` against
         # `ref == 0`: in the first rows of a large problem neighbours are hundreds of ranges apart and the
@@ -527,6 +527,15 @@ class Runner:
         cols = np.arange(self.p)[None, :]
         same_pattern = bool(np.all(got[cols >= n0[:, None]] == 0) and np.all(ref[cols >= n0[:, None]] == 0)
                             and np.all(got[np.arange(rows.size), n0 - 1] > 0))
+        self.parity_extra = None
+        if self.wl["layout"] == "zy":
+            # latent neighbours without nugget plus a duplicated location: cond ~ 1e5-1e6, two correct fp64 results
+            # differ by cond * eps.  The arbiter is the __float128 mode of the oracle on the same fp64 inputs.
+            pr.run(host_threads(), mode=2)
+            quad = pr.Lentries().copy()
+            sc = np.abs(quad).max(axis=1, keepdims=True)
+            self.parity_extra = {"gpu_vs_float128": self.allmax(float((np.abs(got - quad) / sc).max())),
+                                 "fp64_oracle_vs_float128": self.allmax(float((np.abs(ref - quad) / sc).max()))}
         return self.allmax(err if same_pattern else 1.0), rows.size
 
     def e2e(self, steps):
@@ -738,6 +747,8 @@ def main():
     perr, nsamp = R.parity_sample()
     roofline["parity_max_err"] = perr
     roofline["parity"] = f"max row-scaled |U - oracle| over {nsamp} sampled rows per rank, MAX over ranks (bar 1e-10)"
+    if R.parity_extra:
+        roofline["parity_ill_conditioned_layout"] = R.parity_extra
 
     e2e_steps = max(3, min(args.steps, 10))
     em = R.e2e(e2e_steps)
@@ -780,8 +791,37 @@ def main():
             R.h.loglik_z(wl["covType"], R.pb["covparms"], None, None, None)
         R.barrier()
         e2e["loglik_e2e_resident_evals_per_s"] = ll_steps / R.allmax(time.perf_counter() - t0)
-        e2e["loglik_e2e_what"] = ("gpv_loglik_z per rank with host buffers (nuggets, tau, z up; 6 doubles back), and its "
-                                  "estimation-loop form (data resident on the handle, only covparms go up)")
+        e2e["loglik_e2e_what"] = ("gpv_loglik_z per rank with host buffers (ALL nuggets, tau, z up on every rank; 6 doubles "
+                                  "back), and its estimation-loop form (data resident on the handle, only covparms go up)")
+        if world > 1:
+            # the multi-process form of the same call: every rank uploads only ITS slice, the slices are exchanged over
+            # NVLink (grouped NCCL broadcasts inside the library), the partial sums are all-reduced (gpv_loglik_z_dist)
+            try:
+                from gpvecchia_b200 import shard
+                uid = torch.from_numpy(G.UHandle.dist_unique_id().copy()).to(R.dev) if rank == 0 else \
+                    torch.zeros(128, dtype=torch.uint8, device=R.dev)
+                dist.broadcast(uid, src=0)
+                R.h.dist_init(uid.cpu().numpy(), rank, world)
+                cuts = shard.uniform_cuts(n_total, world)
+                a, b = int(cuts[rank]), int(cuts[rank + 1])
+                nug_s = torch.from_numpy(np.ascontiguousarray(R.pb["nug_all"][a:b])).pin_memory().numpy()
+                tau_s = torch.from_numpy(np.ascontiguousarray(R.pb["nug_obs"][a:b])).pin_memory().numpy()
+                z_s = torch.from_numpy(np.ascontiguousarray(R.pb["z"][a:b])).pin_memory().numpy()
+                for _ in range(2):
+                    rd = R.h.loglik_z_dist(wl["covType"], R.pb["covparms"], nug_s, tau_s, z_s, cuts, cuts)
+                R.barrier()
+                t0 = time.perf_counter()
+                for _ in range(ll_steps):
+                    rd = R.h.loglik_z_dist(wl["covType"], R.pb["covparms"], nug_s, tau_s, z_s, cuts, cuts)
+                R.barrier()
+                e2e["loglik_e2e_nvlink_evals_per_s"] = ll_steps / R.allmax(time.perf_counter() - t0)
+                e2e["loglik_e2e_nvlink_rel_err"] = abs(rd["loglik"] - llv["loglik"]) / abs(llv["loglik"])
+                e2e["loglik_e2e_nvlink_what"] = ("gpv_loglik_z_dist: each rank uploads 1/N of nuggets, tau and z from pinned "
+                                                 "host memory, NCCL broadcasts over NVLink fill the rest, one ncclAllReduce "
+                                                 "of the partial sums; every rank returns the whole log-likelihood")
+            except G.GpvError as ex:
+                e2e["loglik_e2e_nvlink_evals_per_s"] = None
+                e2e["loglik_e2e_nvlink_what"] = f"unavailable: {ex}" 
 
     extras = {"input_generation_s": R.t_gen, "handle_creation_s": R.t_create}
     if not args.no_extras:

@@ -27,6 +27,7 @@ EXPORTED = [
     "gpv_multi_create", "gpv_multi_destroy", "gpv_multi_num_devices", "gpv_multi_packed_len",
     "gpv_multi_row_cuts", "gpv_multi_set_revcond", "gpv_multi_u_values_packed",
     "gpv_multi_loglik_numerator", "gpv_multi_loglik_z", "gpv_set_last_error",
+    "gpv_dist_unique_id", "gpv_dist_init", "gpv_dist_finalize", "gpv_loglik_z_dist",
 ]
 
 
@@ -134,6 +135,14 @@ def _load():
     L.gpv_multi_loglik_numerator.restype = i32
     L.gpv_multi_loglik_z.argtypes = [vp, cp, vp, i32, vp, vp, vp, i64, vp]
     L.gpv_multi_loglik_z.restype = i32
+    L.gpv_dist_unique_id.argtypes = [vp]
+    L.gpv_dist_unique_id.restype = i32
+    L.gpv_dist_init.argtypes = [vp, vp, i32, i32]
+    L.gpv_dist_init.restype = i32
+    L.gpv_dist_finalize.argtypes = [vp]
+    L.gpv_dist_finalize.restype = i32
+    L.gpv_loglik_z_dist.argtypes = [vp, cp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.gpv_loglik_z_dist.restype = i32
     L.gpv_set_last_error.argtypes = [cp]
     L.gpv_set_last_error.restype = None
     # host-only self-test hooks of the general-nu machinery (single points; not a compute path)

@@ -572,13 +572,19 @@ struct gpv_handle {
   int64_t n_launch = 0, stats_base = 0;
   bool ev_valid = false;
   const char* last_kernel = "";
+  // multi-process exchange (gpv_dist.inc): NCCL communicator of this handle's rank, or null
+  void* comm = nullptr;
+  int dist_rank = 0, dist_world = 1;
+  bool reduce_over_ranks = false;
 };
 static const int kObsBlocks = 296;
 static const int kTrivBlocks = 296;
 
+static void dist_release(gpv_handle* h);   // gpv_dist.inc
 static void free_handle(gpv_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  dist_release(h);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
   cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
   cudaFree(h->d_trivlist); cudaFree(h->d_order); cudaFree(h->d_locs_s); cudaFree(h->d_nug_s); cudaFree(h->d_zloc_rows); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
@@ -1337,6 +1343,7 @@ extern "C" gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, co
                        nullptr, nfail, first_fail);
 }
 
+static gpv_status dist_allreduce_loglik(gpv_handle* h);   // gpv_dist.inc
 static gpv_status loglik_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
                                 const double* nuggets, const double* nuggets_obsord, const double* zord,
                                 int64_t n, int64_t skip_rows, int include_obs_terms, double out5[5]) {
@@ -1383,6 +1390,7 @@ static gpv_status loglik_common(gpv_handle* h, const char* covType, const double
                                                   kObsBlocks, h->d_nfail, h->d_loglik, 5);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  if (h->reduce_over_ranks) { s = dist_allreduce_loglik(h); if (s) return s; }
   CUDA_TRY(cudaMemcpyAsync(out5, h->d_loglik, sizeof(double) * 5, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return GPV_OK;
@@ -1590,3 +1598,4 @@ extern "C" double gpv_selftest_table_eval_host(double w, double sig2, double ran
 #include "gpv_csc.inc"
 #include "gpv_mat.inc"
 #include "gpv_ic0.inc"
+#include "gpv_dist.inc"

@@ -254,6 +254,36 @@ class UHandle:
         return dict(loglik=float(out[0]), quadform_num=float(out[1]), logdet_num=float(out[2]),
                     quadform_denom=float(out[3]), logdet_denom=float(out[4]), nfail=int(out[5]))
 
+    # ---- multi-process runs: slices exchanged over NVLink (NCCL), partial sums all-reduced (gpv_dist.inc) ----
+    @staticmethod
+    def dist_unique_id():
+        """128 bytes from rank 0 (ncclGetUniqueId) that the caller carries to every rank."""
+        buf = np.zeros(128, dtype=np.uint8)
+        check(lib.gpv_dist_unique_id(_ptr(buf)))
+        return buf
+
+    def dist_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(np.asarray(unique_id, dtype=np.uint8))
+        if uid.size != 128:
+            raise ValueError("unique_id must be the 128 bytes of dist_unique_id()")
+        check(lib.gpv_dist_init(self._h, _ptr(uid), int(rank), int(world)))
+        self._dist = (int(rank), int(world))
+
+    def loglik_z_dist(self, covType, covparms, nuggets_slice, tau_slice, z_slice, loc_cuts, obs_cuts):
+        """Whole log-likelihood over all ranks from each rank's SLICE of nuggets.all.ord / nuggets.ord / zord
+        (gpv_loglik_z_dist); every rank returns the complete value.  None slices reuse the previous call's data."""
+        cov = _f64(covparms)
+        ns = None if nuggets_slice is None else _f64(nuggets_slice)
+        ts = None if tau_slice is None else _f64(tau_slice)
+        zs = None if z_slice is None else _f64(z_slice)
+        lc = None if loc_cuts is None else np.ascontiguousarray(np.asarray(loc_cuts, dtype=np.int64))
+        oc = None if obs_cuts is None else np.ascontiguousarray(np.asarray(obs_cuts, dtype=np.int64))
+        out = np.zeros(6, dtype=np.float64)
+        check(lib.gpv_loglik_z_dist(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(ns), _ptr(ts), _ptr(zs),
+                                    _ptr(lc), _ptr(oc), _ptr(out)))
+        return dict(loglik=float(out[0]), quadform_num=float(out[1]), logdet_num=float(out[2]),
+                    quadform_denom=float(out[3]), logdet_denom=float(out[4]), nfail=int(out[5]))
+
     def u_dev(self, covType, covparms, d_nuggets, d_out=None, packed=False, d_zord=None, skip_rows=0,
               d_loglik=None, stream=None):
         """Device-pointer variant (ints are raw device addresses, e.g. torch_tensor.data_ptr())."""

@@ -195,6 +195,24 @@ int64_t gpv_launch_count(void);
  * into `out`; likelihood partial sums are added on the host in device order.  There is no
  * inter-GPU data path (rows are independent), so no collective is involved.  `devices` may repeat
  * an ordinal (several shards on one GPU). */
+/* ---- multi-process runs (one process per GPU): the path's one exchange step ---------------------------------
+ * Every rank needs ALL per-location nuggets and all of z (a row's neighbours may be any earlier location) but only
+ * its own rows of everything else.  gpv_loglik_z_dist takes each rank's SLICE of those vectors, exchanges the
+ * slices GPU to GPU over NVLink / NVSwitch (grouped NCCL broadcasts) and combines the likelihood partial sums with
+ * one ncclAllReduce, so that every rank returns the complete log-likelihood -- the north-star's "partial sums
+ * combined by an NCCL allreduce over NVLink" behind the C ABI.  NCCL is loaded at run time (libnccl.so.2); without
+ * it these entry points return GPV_ERR_UNSUPPORTED.  Bootstrap as in any NCCL program: rank 0 calls
+ * gpv_dist_unique_id, the caller carries the 128 bytes to the other ranks, every rank calls gpv_dist_init on ITS
+ * shard handle (gpv_create_shard / a row range).  loc_cuts / obs_cuts: world + 1 entries, identical on all ranks;
+ * rank r passes entries [loc_cuts[r], loc_cuts[r+1]) of nuggets.all.ord and [obs_cuts[r], obs_cuts[r+1]) of
+ * nuggets.ord / zord.  NULL slices on every rank reuse the vectors of the previous call (estimation loop). */
+gpv_status gpv_dist_unique_id(void* id128 /* 128 bytes out */);
+gpv_status gpv_dist_init(gpv_handle* h, const void* id128, int rank, int world);
+gpv_status gpv_dist_finalize(gpv_handle* h);
+gpv_status gpv_loglik_z_dist(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
+                             const double* nuggets_slice, const double* tau_slice, const double* z_slice,
+                             const int64_t* loc_cuts, const int64_t* obs_cuts, double out[6]);
+
 typedef struct gpv_multi gpv_multi;
 gpv_status gpv_multi_create(gpv_multi** out, int64_t Nlocs, int p, int d, const double* locs,
                             const int32_t* revNNarray, const void* revCondOnLatent,

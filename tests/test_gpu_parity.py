@@ -854,3 +854,31 @@ def test_locality_layer_changes_the_order_of_work_not_the_results(layout, monkey
             assert b[7] is not None and np.array_equal(a[7], b[7])
         assert np.allclose(np.asarray(a[6][:2], dtype=float), np.asarray(b[6][:2], dtype=float), rtol=1e-12, atol=0)
         assert a[6][2] == b[6][2]
+
+
+def test_distributed_likelihood_entry_point_on_one_rank():
+    """gpv_loglik_z_dist (gpv_dist.inc) with a one-rank NCCL communicator: the slices are the whole vectors, the
+    broadcasts and the all-reduce run on one device -- every line of the multi-process path except a second GPU
+    (tools/dist_check.py runs it under torchrun on 2+ GPUs).  Must equal gpv_loglik_z."""
+    n, m = 20000, 15
+    va = _problem(n, m, 2, "z", stream=140)
+    prep = va["U_prep"]
+    z = H.make_data(n, stream=140)
+    tau = H.make_nuggets(n, stream=140)
+    cp = [1.1, H.default_range(n, 2), 0.8]
+    with G.UHandle(va["locsord"], prep["revNNarray"], prep["revCond"], obs=va["obs"]) as h:
+        want = h.loglik_z("matern", cp, tau, tau, z)
+        try:
+            h.dist_init(G.UHandle.dist_unique_id(), 0, 1)
+        except G.GpvError as e:
+            if e.status == 5:
+                pytest.skip("NCCL not loadable on this box")
+            raise
+        cuts = np.array([0, n], dtype=np.int64)
+        got = h.loglik_z_dist("matern", cp, tau, tau, z, cuts, cuts)
+        again = h.loglik_z_dist("matern", [1.3, cp[1], 1.5], None, None, None, None, None)   # resident data, new covparms
+        want2 = h.loglik_z("matern", [1.3, cp[1], 1.5], tau, tau, z)
+    for k in ("loglik", "quadform_num", "logdet_num", "quadform_denom", "logdet_denom"):
+        assert abs(got[k] - want[k]) <= 1e-13 * abs(want[k]), k
+        assert abs(again[k] - want2[k]) <= 1e-13 * abs(want2[k]), k
+    assert got["nfail"] == want["nfail"] == 0

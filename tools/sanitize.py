@@ -5,8 +5,11 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import gpvecchia_b200 as G
 from gpvecchia_b200 import harness as H
 
-for (n, m, d, layout) in ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"), (500, 9, 2, "zy"), (200, 5, 5, "z"),
-                          (300, 20, 2, "z"), (300, 25, 2, "z"), (300, 31, 2, "z"), (300, 40, 3, "z"), (300, 20, 3, "zy")):
+CASES = ((600, 30, 2, "z"), (400, 12, 3, "z"), (300, 40, 2, "z"), (500, 9, 2, "zy"), (200, 5, 5, "z"),
+         (300, 20, 2, "z"), (300, 25, 2, "z"), (300, 31, 2, "z"), (300, 40, 3, "z"), (300, 20, 3, "zy"))
+# every case twice: plain path, and with the locality layer forced on (Morton-sorted replica + permuted set list)
+for loc, (n, m, d, layout) in [(l, c) for l in ("0", "1") for c in CASES]:
+    os.environ["GPV_LOCALITY"] = loc
     locs = H.make_locs(n, d, stream=1)
     if layout == "zy":
         locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
