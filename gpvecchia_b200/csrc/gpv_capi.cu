@@ -223,10 +223,20 @@ __global__ void gather_locs_kernel(const double* __restrict__ locs, const int32_
   const int64_t o = order[i];
   for (int c = 0; c < d; ++c) out[i * d + c] = locs[o * d + c];
 }
-__global__ void gather_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ order, int64_t N,
-                                  double* __restrict__ out) {
+// per call: the per-location vectors in replica order -- nuggets always, z (through zsrc = obsrank o order, composed
+// once per handle) when the likelihood is wanted: one pass, two random gathers
+__global__ void gather_percall_kernel(const double* __restrict__ nuggets, const int32_t* __restrict__ order,
+                                      const double* __restrict__ zord, const int32_t* __restrict__ zsrc, int64_t N,
+                                      double* __restrict__ nug_out, double* __restrict__ z_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) out[i] = src[order[i]];
+  if (i >= N) return;
+  nug_out[i] = nuggets[order[i]];
+  if (z_out != nullptr) { const int r = zsrc[i]; z_out[i] = r >= 0 ? zord[r] : 0.0; }
+}
+__global__ void compose_index_kernel(const int32_t* __restrict__ obsrank, const int32_t* __restrict__ order, int64_t N,
+                                     int32_t* __restrict__ zsrc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) zsrc[i] = obsrank[order[i]];
 }
 // set s of the processing order = set perm[s] of the row order: its row number and its (renamed) neighbour ids
 __global__ void permute_sets_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ rowmap_in,
@@ -530,6 +540,7 @@ struct gpv_handle {
   bool locality = false;
   bool mapped = false;                // the set kernel reads the set list (split || locality)
   int32_t* d_order = nullptr;         // [Nlocs] location held at position i of the sorted replica
+  int32_t* d_zsrc = nullptr;          // [Nlocs] obsrank[d_order[i]]: where z of replica position i sits in zord, or -1
   double* d_locs_s = nullptr;         // [Nlocs][d] sorted replica of locs
   double* d_nug_s = nullptr;          // [Nlocs] per call: nuggets in replica order
   double* d_zloc_rows = nullptr;      // [Nlocs] z per location in the ORIGINAL order (n0 <= 1 rows of a split layout)
@@ -587,7 +598,7 @@ static void free_handle(gpv_handle* h) {
   dist_release(h);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
   cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
-  cudaFree(h->d_trivlist); cudaFree(h->d_order); cudaFree(h->d_locs_s); cudaFree(h->d_nug_s); cudaFree(h->d_zloc_rows); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
+  cudaFree(h->d_trivlist); cudaFree(h->d_order); cudaFree(h->d_zsrc); cudaFree(h->d_locs_s); cudaFree(h->d_nug_s); cudaFree(h->d_zloc_rows); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
   cudaFree(h->d_zloc); cudaFree(h->d_flag); cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
   cudaFree(h->d_first_fail); cudaFree(h->d_table);
@@ -991,6 +1002,14 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
         if (!h->d_cond_full) e = cudaMalloc(&h->d_cond_full, sizeof(uint64_t) * (size_t)nsets);
         h->locality = true;
         h->mapped = true;
+        if (e == cudaSuccess && h->d_obsrank) {
+          e = cudaMalloc(&h->d_zsrc, sizeof(int32_t) * (size_t)Nlocs);
+          if (e == cudaSuccess) {
+            compose_index_kernel<<<grid_for(Nlocs, 256), 256, 0, h->stream>>>(h->d_obsrank, h->d_order, Nlocs, h->d_zsrc);
+            g_launches++;
+            e = cudaStreamSynchronize(h->stream);
+          }
+        }
       } else {
         cudaFree(rowmap2); cudaFree(nn2);
       }
@@ -1118,7 +1137,9 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.nuggets = d_nuggets;
   if (h->locality) {
     if (set_begin == 0) {               // once per call (the chunks of a call share it)
-      gather_f64_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_nuggets, h->d_order, h->Nlocs, h->d_nug_s);
+      if (want_loglik && !h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
+      gather_percall_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_nuggets, h->d_order, d_zord, h->d_zsrc, h->Nlocs,
+                                                                     h->d_nug_s, want_loglik ? h->d_zloc : nullptr);
       g_launches++;
     }
     q.nuggets = h->d_nug_s;
@@ -1129,9 +1150,11 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.zloc = nullptr; q.full_z = 0; q.skip_rows = skip_rows;
   if (want_loglik) {
     // z per location, expanded once per call so the set kernel can prefetch it like a nugget
-    if (!h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
-    expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, h->locality ? h->d_order : nullptr, h->Nlocs, h->d_zloc);
-    g_launches++;
+    if (!h->locality) {                 // (with the locality layer z came with the nuggets, above)
+      if (!h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
+      expand_z_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_zord, h->d_obsrank, nullptr, h->Nlocs, h->d_zloc);
+      g_launches++;
+    }
     q.zloc = h->d_zloc;
     if (h->locality && h->split && h->ntriv > 0) {
       if (!h->d_zloc_rows) CUDA_TRY(cudaMalloc(&h->d_zloc_rows, sizeof(double) * (size_t)h->Nlocs));
