@@ -23,6 +23,10 @@ struct gpv_multi {
   std::vector<int64_t> off;        // packed offsets, size ndev + 1
   int64_t Nlocs = 0, n_obs = 0;
   int p = 0;
+  // NVLink exchange between the devices of this process (gpv_dist_*): each device uploads 1/ndev of the per-call
+  // vectors of a likelihood call and NCCL broadcasts fill the rest, instead of ndev full uploads through one host
+  bool dist = false;
+  std::vector<int64_t> loc_cuts, obs_cuts;
 };
 
 extern "C" void gpv_set_last_error(const char* msg);   // gpv_capi.cu
@@ -91,6 +95,24 @@ extern "C" gpv_status gpv_multi_create(gpv_multi** out, int64_t Nlocs, int p, in
   m->off.assign(ndev + 1, 0);
   for (int i = 0; i < ndev; ++i) m->off[i + 1] = m->off[i] + gpv_packed_len(m->h[i]);
   if (obs) for (int64_t i = 0; i < Nlocs; ++i) m->n_obs += (obs[i] != 0 && obs[i] != INT32_MIN);
+  // one NCCL communicator over the devices (distinct ordinals, no empty shard): optional, the host path stays
+  bool distinct = ndev > 1 && m->n_obs > 0;
+  for (int i = 0; i < ndev && distinct; ++i) {
+    if (m->cut[i + 1] <= m->cut[i]) distinct = false;
+    for (int j = 0; j < i; ++j) if (m->dev[j] == m->dev[i]) distinct = false;
+  }
+  if (distinct) {
+    char uid[128];
+    if (gpv_dist_unique_id(uid) == GPV_OK &&
+        run_all(ndev, [&](int i) { return gpv_dist_init(m->h[i], uid, i, ndev); }) == GPV_OK) {
+      m->dist = true;
+      m->loc_cuts.resize(ndev + 1);
+      m->obs_cuts.resize(ndev + 1);
+      for (int i = 0; i <= ndev; ++i) { m->loc_cuts[i] = Nlocs * i / ndev; m->obs_cuts[i] = m->n_obs * i / ndev; }
+    } else {
+      for (auto* hh : m->h) gpv_dist_finalize(hh);
+    }
+  }
   *out = m;
   return GPV_OK;
 }
@@ -231,6 +253,17 @@ extern "C" gpv_status gpv_multi_loglik_z(gpv_multi* m, const char* covType, cons
   if (!m || !out) { gpv_set_last_error("gpv_multi_loglik_z: null argument"); return GPV_ERR_ARG; }
   const int nd = (int)m->h.size();
   std::vector<double> parts(6 * (size_t)nd, 0.0);
+  if (m->dist && nuggets && nuggets_obsord && zord && n == m->n_obs) {
+    // every device uploads its slice, the slices travel over NVLink, the partial sums are all-reduced on the
+    // devices: each shard returns the complete result
+    gpv_status sd = run_all(nd, [&](int i) {
+      return gpv_loglik_z_dist(m->h[i], covType, covparms, ncov, nuggets + m->loc_cuts[i], nuggets_obsord + m->obs_cuts[i],
+                               zord + m->obs_cuts[i], m->loc_cuts.data(), m->obs_cuts.data(), &parts[6 * (size_t)i]);
+    });
+    if (sd != GPV_OK) return sd;
+    for (int k = 0; k < 6; ++k) out[k] = parts[k];
+    return GPV_OK;
+  }
   gpv_status st = run_all(nd, [&](int i) {
     return gpv_loglik_z(m->h[i], covType, covparms, ncov, nuggets, nuggets_obsord, zord, n, i == 0 ? 1 : 0,
                         &parts[6 * (size_t)i]);
