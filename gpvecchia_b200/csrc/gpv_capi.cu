@@ -542,6 +542,11 @@ struct gpv_handle {
   int32_t* d_order = nullptr;         // [Nlocs] location held at position i of the sorted replica
   int32_t* d_zsrc = nullptr;          // [Nlocs] obsrank[d_order[i]]: where z of replica position i sits in zord, or -1
   double* d_locs_s = nullptr;         // [Nlocs][d] sorted replica of locs
+  // a second set list in ONE Morton order over all sets, for whole-range launches (device-resident call, likelihood,
+  // pageable output): the replica is then swept once per launch instead of once per output chunk
+  int32_t* d_rowmap_g = nullptr;
+  int32_t* d_nn_full_g = nullptr;
+  uint64_t* d_cond_full_g = nullptr;
   double* d_nug_s = nullptr;          // [Nlocs] per call: nuggets in replica order
   double* d_zloc_rows = nullptr;      // [Nlocs] z per location in the ORIGINAL order (n0 <= 1 rows of a split layout)
   // per-call scratch (allocated lazily, reused)
@@ -597,7 +602,7 @@ static void free_handle(gpv_handle* h) {
   cudaSetDevice(h->device);
   dist_release(h);
   cudaFree(h->d_locs); cudaFree(h->d_nn); cudaFree(h->d_cond); cudaFree(h->d_row_off);
-  cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full);
+  cudaFree(h->d_obsrank); cudaFree(h->d_obs_excl); cudaFree(h->d_csc_rank); cudaFree(h->d_csc_cond); cudaFree(h->d_rowmap); cudaFree(h->d_nn_full); cudaFree(h->d_cond_full); cudaFree(h->d_rowmap_g); cudaFree(h->d_nn_full_g); cudaFree(h->d_cond_full_g);
   cudaFree(h->d_trivlist); cudaFree(h->d_order); cudaFree(h->d_zsrc); cudaFree(h->d_locs_s); cudaFree(h->d_nug_s); cudaFree(h->d_zloc_rows); cudaFree(h->d_nuggets); cudaFree(h->d_tau); cudaFree(h->d_zord);
   cudaFree(h->d_zloc); cudaFree(h->d_flag); cudaFree(h->d_out); cudaFree(h->d_out2); cudaFree(h->d_zent); cudaFree(h->d_partials);
   cudaFree(h->d_obs_partials); cudaFree(h->d_loglik); cudaFree(h->d_nfail);
@@ -630,6 +635,11 @@ static gpv_status upload_cond(gpv_handle* h, const void* host) {
     if (h->mapped && nmapped > 0) {
       gather_cond_rows_kernel<<<grid_for(nmapped, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap, nmapped,
                                                                              h->d_cond_full);
+      if (h->d_rowmap_g) {
+        gather_cond_rows_kernel<<<grid_for(nmapped, 256), 256, 0, h->stream>>>(h->d_cond, h->d_rowmap_g, nmapped,
+                                                                               h->d_cond_full_g);
+        g_launches++;
+      }
       g_launches++;
     }
     int not_pure = 0;
@@ -993,6 +1003,21 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
         permute_sets_kernel<<<grid_for(nsets * p, 256), 256, 0, h->stream>>>(v_out, h->split ? h->d_rowmap : nullptr,
                                                                               h->split ? h->d_nn_full : h->d_nn, inv, nsets, p, rowmap2, nn2);
         g_launches += 3;
+        if (e == cudaSuccess && h->nchunks > 1) {
+          // (iii) and once more in ONE order over all sets (no chunk number in the key)
+          e = cudaMalloc(&h->d_rowmap_g, sizeof(int32_t) * (size_t)nsets);
+          if (e == cudaSuccess) e = cudaMalloc(&h->d_nn_full_g, sizeof(int32_t) * (size_t)nsets * p);
+          if (e == cudaSuccess) e = cudaMalloc(&h->d_cond_full_g, sizeof(uint64_t) * (size_t)nsets);
+          if (e == cudaSuccess) {
+            morton_key_kernel<<<grid_for(nsets, 256), 256, 0, h->stream>>>(h->d_locs, Nlocs, d, d_box, h->split ? h->d_rowmap : nullptr,
+                                                                           row_begin, nsets, nullptr, 0, k_in, v_in);
+            e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)nsets, 0, 32, h->stream);
+            permute_sets_kernel<<<grid_for(nsets * p, 256), 256, 0, h->stream>>>(v_out, h->split ? h->d_rowmap : nullptr,
+                                                                                  h->split ? h->d_nn_full : h->d_nn, inv, nsets, p,
+                                                                                  h->d_rowmap_g, h->d_nn_full_g);
+            g_launches += 3;
+          }
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       }
       cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(inv); cudaFree(d_box); cudaFree(d_chunks); cudaFree(tmp);
@@ -1132,7 +1157,9 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
   q.nsets = set_count;
   q.set_base = set_begin;
-  q.rowmap = h->mapped ? h->d_rowmap + set_begin : nullptr;
+  // whole-range launches of a handle with the locality layer run in one global Morton order
+  const bool global_order = h->d_rowmap_g != nullptr && set_begin == 0 && set_count == all_sets;
+  q.rowmap = h->mapped ? (global_order ? h->d_rowmap_g : h->d_rowmap + set_begin) : nullptr;
   q.locs = h->locality ? h->d_locs_s : h->d_locs;
   q.nuggets = d_nuggets;
   if (h->locality) {
@@ -1144,8 +1171,8 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
     }
     q.nuggets = h->d_nug_s;
   }
-  q.nn = (h->mapped ? h->d_nn_full : h->d_nn) + set_begin * h->p;
-  q.cond = (h->mapped ? h->d_cond_full : h->d_cond) + set_begin;
+  q.nn = global_order ? h->d_nn_full_g : (h->mapped ? h->d_nn_full : h->d_nn) + set_begin * h->p;
+  q.cond = global_order ? h->d_cond_full_g : (h->mapped ? h->d_cond_full : h->d_cond) + set_begin;
   q.out = d_out; q.row_off = packed ? h->d_row_off : nullptr;
   q.zloc = nullptr; q.full_z = 0; q.skip_rows = skip_rows;
   if (want_loglik) {
