@@ -697,6 +697,54 @@ def test_cfg2_full_size_properties():
     assert _rowscaled_err(L[rows], pr.Lentries()) < VAL_TOL
 
 
+@pytest.mark.parametrize("n,m,d,covType,cp_tail", [
+    (4_000_000, 30, 2, "matern", [0.8]),            # BASELINE configs[2] shape: general-nu branch, locality layer on
+    (1_000_000, 40, 3, "esqe", [0.5, None]),        # BASELINE configs[3] shape: 16-lane groups, 3-D, esqe
+])
+def test_cfg3_cfg4_large_size_properties(n, m, d, covType, cp_tail):
+    """The other large BASELINE shapes at sizes the oracle cannot run in seconds: size-independent properties on
+    everything (idempotence, packed order, the scale property, fused sums against the values, zero fill) and a
+    3 000-row sample against the oracle.  n = 4e6 keeps the GPU suite short; bench.py runs cfg3 at its full 1e7 with
+    the same sample check inside the run."""
+    locs = H.make_locs(n, d, stream=3)
+    revNN = H.ordered_nn_gpu(locs, m)
+    revCond = np.zeros(revNN.shape, dtype=np.int32)
+    revCond[revNN == 0] = np.iinfo(np.int32).min
+    revCond[:, -1] = 1
+    nug = H.make_nuggets(n, stream=3)
+    z = H.make_data(n, stream=3)
+    rng_ = H.default_range(n, d)
+    cp = [1.0, rng_] + [rng_ if v is None else v for v in cp_tail]
+    cp4 = list(cp)
+    cp4[0] *= 4.0
+    if covType == "esqe":
+        cp4[2] *= 4.0
+    with G.UHandle(locs, revNN, revCond, obs=np.ones(n, dtype=np.int32)) as h:
+        a = h.U_NZentries(covType, cp, nug, nug)
+        name = h.last_kernel_name()
+        packed, nf, _ = h.values_packed(covType, cp, nug, nug, zentries_tail=False)
+        b = h.U_NZentries(covType, cp4, 4.0 * nug, 4.0 * nug)
+        ll = h.loglik_z(covType, cp, nug, nug, z)
+    assert name.startswith("u_band<G=%d" % (8 if m == 30 else 16)) and ("general" in name) == (covType == "matern")
+    L = a["Lentries"]
+    assert a["nfail"] == 0 and nf == 0 and ll["nfail"] == 0
+    assert np.array_equal(packed, L.ravel()[(revNN[:, ::-1] != 0).ravel()])    # packed a9 order (chunked pipeline, per-chunk order)
+    n0 = (revNN != 0).sum(axis=1)
+    diag = L[np.arange(n), n0 - 1]
+    assert np.all(diag > 0) and np.all(np.isfinite(L))
+    assert np.all(L[n0 < m + 1][:, -1] == 0)
+    assert _rowscaled_err(b["Lentries"] * 2.0, L) < 1e-12                      # cov -> 4 cov => U -> U/2
+    ld = -2.0 * np.log(diag).sum() + np.log(nug).sum()
+    assert abs(ld - ll["logdet_num"]) <= 1e-10 * abs(ld)
+    rng = np.random.default_rng(1)
+    rows = np.sort(rng.choice(np.arange(m + 1, n), 3000, replace=False))
+    rc = revCond[rows].astype(np.float64)
+    rc[revCond[rows] < 0] = np.nan
+    pr = O.RowsProblem(locs, revNN[rows], rc, 0, nug, covType, np.array(cp))
+    pr.run(O.max_threads())
+    assert _rowscaled_err(L[rows], pr.Lentries()) < VAL_TOL
+
+
 def test_randomised_sweep_against_oracle():
     # seeded random shapes: set size, dimension, covariance, conditioning mask, missing pattern,
     # nugget vector -- every case against the CPU restatement (values) and its failure count
