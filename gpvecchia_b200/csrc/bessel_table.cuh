@@ -28,6 +28,12 @@ namespace gpv {
 #ifndef GPV_TAB_SUBBITS
 #define GPV_TAB_SUBBITS 2
 #endif
+#ifndef GPV_TAB_WIN_OCT
+#define GPV_TAB_WIN_OCT 24      // octaves of w in the shared-memory window of the band kernels
+#endif
+#ifndef GPV_TAB_WIN_TOP
+#define GPV_TAB_WIN_TOP 8       // the window ends this many octaves above the median squared neighbour distance
+#endif
 constexpr int kTabDeg = GPV_TAB_DEG;
 constexpr int kTabSubBits = GPV_TAB_SUBBITS;   // 2^bits intervals per octave of w
 constexpr int kTabSub = 1 << kTabSubBits;

@@ -30,7 +30,7 @@ inline void nu_constants(double nu, double sig2, CovTable* t) {
 // s = d / range >= kTabSSplit the table holds exp(+s) cov (w_split is an interval edge)
 // win_top_exp: biased exponent of the highest octave of w the shared-memory window should hold (from the
 // handle's histogram of neighbour distances), or < 0: the window ends at the top of the table.
-constexpr int kTabWindow = 24 * kTabSub;            // intervals in the window: 24 octaves of w (4096 : 1 in distance)
+constexpr int kTabWindow = GPV_TAB_WIN_OCT * kTabSub;   // intervals in the window (24 octaves of w: 4096 : 1 in distance)
 inline void general_table_range(double range, double w_max, CovTable* tp, int win_top_exp = -1) {
   CovTable& t = *tp;
   double wmax = (w_max > 0.0 && std::isfinite(w_max)) ? w_max : 1.0;

@@ -952,7 +952,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       // 2^-15.x w50 (pairs 200 times closer than the typical neighbour: a per-mille event per set)
       int med = 0;
       while (med < 2047 && 2 * (acc + hist[med]) < total) { acc += hist[med]; ++med; }
-      h->win_top_exp = med + 8;
+      h->win_top_exp = med + GPV_TAB_WIN_TOP;
     }
   }
   // locality layer: on for large N (per-location data beyond ~48 MB no longer sit in the L2 next to the streams);
@@ -1265,7 +1265,7 @@ static gpv_status ensure_tau(gpv_handle* h, int64_t n) {
   h->nug_resident = false;
   return GPV_OK;
 }
-static gpv_status run_zentries(gpv_handle* h, const double* nuggets_obsord, int64_t n) {
+static gpv_status run_zentries(gpv_handle* h, const double* nuggets_obsord, int64_t n) {   // NULL: d_tau is resident
   if (n <= 0) return GPV_OK;
   // A whole-range handle takes the nuggets of all its observations.  A row shard (gpv_create_shard / a row range)
   // may be given the nuggets of ANY contiguous slice of the observations -- normally those located in its rows --
@@ -1274,8 +1274,10 @@ static gpv_status run_zentries(gpv_handle* h, const double* nuggets_obsord, int6
   const bool whole = (h->nrows == h->Nlocs);
   if (h->have_obs && h->n_obs != 0 && (whole ? n != h->n_obs : n > h->n_obs))
     return fail(GPV_ERR_ARG, "n=%lld does not match sum(obs)=%lld", (long long)n, (long long)h->n_obs);
-  gpv_status s = ensure_tau(h, n); if (s) return s;
-  CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  if (nuggets_obsord) {
+    gpv_status s = ensure_tau(h, n); if (s) return s;
+    CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  }
   zentries_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->d_tau, n, h->d_zent);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1313,19 +1315,32 @@ static bool host_buffer_is_pinned(const void* p) {
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
+// Per-location nuggets of a U-values call: uploaded, or (both vectors NULL) the ones gpv_set_scalar_nugget left on
+// the device -- a scalar nugget then costs no 8-bytes-per-location upload per call (createU.R:70-78 builds the
+// two vectors from the scalar on the host).  Sets the device.
+static gpv_status take_nuggets(gpv_handle* h, const double* nuggets, const double* nuggets_obsord, int64_t n) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!nuggets && !nuggets_obsord) {
+    if (!h->nug_resident) return fail(GPV_ERR_ARG, "no nuggets given and none resident on the handle (gpv_set_scalar_nugget)");
+    if (n != 0 && n != h->n_obs) return fail(GPV_ERR_ARG, "n=%lld does not match sum(obs)=%lld", (long long)n, (long long)h->n_obs);
+    return GPV_OK;
+  }
+  if (!nuggets) return fail(GPV_ERR_ARG, "nuggets is null");
+  if (n > 0 && !nuggets_obsord) return fail(GPV_ERR_ARG, "nuggets_obsord is null");
+  h->nug_resident = false;             // d_nuggets / d_tau are shared with the likelihood calls
+  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+  return GPV_OK;
+}
 // shared body of gpv_u_nzentries / gpv_u_values_packed
 static gpv_status u_host_common(gpv_handle* h, const char* covType, const double* covparms, int ncov,
                                 const double* nuggets, const double* nuggets_obsord, int64_t n,
                                 int packed, int ztail, double* out, double* zout, int64_t* nfail,
                                 int64_t* first_fail) {
-  if (!h || !nuggets || !out) return fail(GPV_ERR_ARG, "null argument");
-  if (n > 0 && !nuggets_obsord) return fail(GPV_ERR_ARG, "nuggets_obsord is null");
-  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h || !out) return fail(GPV_ERR_ARG, "null argument");
+  gpv_status s = take_nuggets(h, nuggets, nuggets_obsord, n); if (s) return s;
   CovSetup cs;
-  gpv_status s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
+  s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
-  h->nug_resident = false;             // d_nuggets is shared with the likelihood calls
-  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
   const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
   bool chunked = false;

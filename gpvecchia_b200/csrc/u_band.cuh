@@ -67,7 +67,7 @@ struct BandLayout {
   // (P = 32 does not leave the room)
   static constexpr bool kWideTables = (kMinBlocks == 1) && (kBytesPerBlock + 13312 + 1024 <= 232448);
   static constexpr int kExpStride = kWideTables ? 16 : 1;
-  static constexpr int kGenWin = kWideTables ? 24 * (1 << GPV_TAB_SUBBITS) : 0;   // intervals of the general-nu table kept in shared memory (cov_setup.h kTabWindow)
+  static constexpr int kGenWin = kWideTables ? GPV_TAB_WIN_OCT * (1 << GPV_TAB_SUBBITS) : 0;   // intervals of the general-nu table kept in shared memory (cov_setup.h kTabWindow)
   static_assert(G == 8 || G == 16, "lane groups of 8 or 16");
   static_assert(P > 2 * G && P <= 4 * G, "band-folded kernel: 2G < P <= 4G");
   static_assert(G == 8 || NB == 3, "four bands of 16 lanes do not fit the register file");

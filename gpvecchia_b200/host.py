@@ -173,11 +173,12 @@ class UHandle:
         return out, int(nfail.value), int(first.value)
 
     def values_packed(self, covType, covparms, nuggets, nuggets_obsord, zentries_tail=True, out=None):
-        """allLentries of createU.R:158-160 for this shard, straight from the device."""
+        """allLentries of createU.R:158-160 for this shard, straight from the device.  nuggets = nuggets_obsord
+        = None: the vectors set_scalar_nugget() left on the device."""
         cov = _f64(covparms)
-        nug = _f64(nuggets)
-        tau = _f64(nuggets_obsord)
-        n = tau.size
+        nug = None if nuggets is None else _f64(nuggets)
+        tau = None if nuggets_obsord is None else _f64(nuggets_obsord)
+        n = self.n_obs if tau is None else tau.size
         total = self.packed_len + (2 * n if zentries_tail else 0)
         if out is None:
             out = np.empty(total, dtype=np.float64)
@@ -210,21 +211,25 @@ class UHandle:
         return colptr, rowidx
 
     def values_csc(self, covType, covparms, nuggets, nuggets_obsord, out=None):
-        """dgCMatrix@x of the U columns of this shard's rows (createU.R:152-161 in one call)."""
-        cov, nug, tau = _f64(covparms), _f64(nuggets), _f64(nuggets_obsord)
+        """dgCMatrix@x of the U columns of this shard's rows (createU.R:152-161 in one call).  nuggets =
+        nuggets_obsord = None: the vectors set_scalar_nugget() left on the device."""
+        cov = _f64(covparms)
+        nug = None if nuggets is None else _f64(nuggets)
+        tau = None if nuggets_obsord is None else _f64(nuggets_obsord)
+        n = self.n_obs if tau is None else tau.size
         _, nnz, _ = self.csc_dims()
         if out is None:
             out = np.empty(nnz, dtype=np.float64)
         elif out.size < nnz or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of nnz doubles")
         nfail, first = C.c_int64(0), C.c_int64(-1)
-        check(lib.gpv_u_values_csc(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau), tau.size,
+        check(lib.gpv_u_values_csc(self._h, covType.encode(), _ptr(cov), cov.size, _ptr(nug), _ptr(tau), n,
                                    _ptr(out), C.byref(nfail), C.byref(first)))
         return out, int(nfail.value), int(first.value)
 
     def set_scalar_nugget(self, nugget):
         """nuggets.all.ord / nuggets.ord of a scalar nugget, built on the device (createU.R:70-78); the
-        likelihood calls then take nuggets=None."""
+        likelihood and U-values calls then take nuggets=None."""
         check(lib.gpv_set_scalar_nugget(self._h, float(nugget)))
 
     def loglik_numerator(self, covType, covparms, nuggets, nuggets_obsord, zord, skip_rows=0,
@@ -564,9 +569,15 @@ def createU(vecchia_approx, covparms, nuggets, covmodel="matern", device=0, asse
         covmat, assemble = covmodel, "triplet"
     elif not isinstance(covmodel, str):
         raise TypeError("argument 'covmodel' type not supported")      # createU.R:155
+    scalar_nugget = np.ndim(nuggets) == 0 or np.size(nuggets) == 1
     n, size, latent, ord_, obs, nuggets, nuggets_all_ord, nuggets_ord = _prepare_nuggets(va, nuggets)
     zero_nuggets = bool(np.any(nuggets == 0))
     h = _handle_for(va, device)
+    if scalar_nugget and not zero_nuggets and covmat is None and va["cond_yz"] != "zy" and n > 0:
+        # one scalar crosses the boundary instead of two vectors: the device builds nuggets.all.ord and
+        # nuggets.ord itself (createU.R:70-78: the nugget at observed locations, 0 elsewhere)
+        h.set_scalar_nugget(float(nuggets[0]))
+        nuggets_all_ord = nuggets_ord = None
     restore = False
     if zero_nuggets:                                                   # createU.R:83-86
         revCond = prep["revCond"].copy()

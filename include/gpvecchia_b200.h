@@ -164,7 +164,10 @@ gpv_status gpv_loglik_z(gpv_handle* h, const char* covType, const double* covpar
  * the previous likelihood call on the handle, and nuggets == nuggets_obsord == NULL reuses its nuggets or
  * those of gpv_set_scalar_nugget, which builds nuggets.all.ord / nuggets.ord of a scalar nugget on the
  * device (createU.R:70-78: the nugget at observed locations, 0 elsewhere).  A call then moves ~30 bytes
- * each way.  GPV_ERR_ARG if nothing is resident; any U-values call on the handle drops the nuggets. */
+ * each way.  GPV_ERR_ARG if nothing is resident.  gpv_u_nzentries / gpv_u_values_packed / gpv_u_values_csc
+ * accept nuggets == nuggets_obsord == NULL the same way (a scalar nugget then costs no per-call upload of
+ * 8 bytes per location); a U-values call that is GIVEN nugget vectors replaces the resident ones and drops
+ * the flag. */
 gpv_status gpv_set_scalar_nugget(gpv_handle* h, double nugget);
 
 /* ---- device-resident variants (inputs/outputs already in HBM; asynchronous on `stream`) ------

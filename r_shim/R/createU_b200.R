@@ -68,10 +68,17 @@ createU <- function(vecchia.approx, covparms, nuggets, covmodel = 'matern') {
   obs <- vecchia.approx$obs
   ord <- vecchia.approx$ord
 
-  ## nuggets per ordered location and per ordered observation (createU.R:74-80)
-  nuggets.all <- c(rep_len(nuggets, n), rep(0, sum(latent) - n))
-  ord.all <- if (vecchia.approx$cond.yz == 'zy') c(ord[1:n], ord + n) else ord
-  U <- .b200_U(vecchia.approx, NULL, covparms, nuggets.all[ord.all], nuggets.all[vecchia.approx$ord.z], covmodel)
+  if (length(nuggets) == 1 && vecchia.approx$cond.yz != 'zy' && is.null(getOption("GPvecchia.b200.devices"))) {
+    ## one scalar crosses the boundary: the device builds nuggets.all.ord / nuggets.ord (the nugget at observed
+    ## locations, 0 elsewhere: createU.R:70-78) and the value calls take NULL vectors
+    .Call("_GPvecchia_b200_set_scalar_nugget", .b200_handle(vecchia.approx), nuggets)
+    U <- .b200_U(vecchia.approx, NULL, covparms, NULL, NULL, covmodel)
+  } else {
+    ## nuggets per ordered location and per ordered observation (createU.R:74-80)
+    nuggets.all <- c(rep_len(nuggets, n), rep(0, sum(latent) - n))
+    ord.all <- if (vecchia.approx$cond.yz == 'zy') c(ord[1:n], ord + n) else ord
+    U <- .b200_U(vecchia.approx, NULL, covparms, nuggets.all[ord.all], nuggets.all[vecchia.approx$ord.z], covmodel)
+  }
 
   ## response-first ('zy') layouts carry n dummy latent rows/columns (createU.R:166-171)
   if (vecchia.approx$cond.yz == 'zy') {

@@ -165,8 +165,11 @@ SEXP gpvb200_set_revcond(SEXP ptr, SEXP revCond) {
 
 /* allLentries of createU.R:158-160 (packed U values followed by Zentries), straight from the GPU */
 SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
-  const int64_t n = XLENGTH(nuggets_ord);
   const int multi = is_multi(ptr);
+  /* NULL nuggets (single-device handle): those of _GPvecchia_b200_set_scalar_nugget, already on the device */
+  const int resident = Rf_isNull(nuggets_all_ord) && Rf_isNull(nuggets_ord);
+  if (resident && multi) Rf_error("resident scalar nugget: single-device handle only");
+  const int64_t n = resident ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(nuggets_ord);
   const int64_t len = multi ? gpv_multi_packed_len(get_multi(ptr)) : gpv_packed_len(get_handle(ptr));
   SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(len + 2 * n)));
   int64_t nfail = 0, first = -1;
@@ -174,7 +177,8 @@ SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_or
       ? gpv_multi_u_values_packed(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
                                   REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first)
       : gpv_u_values_packed(get_handle(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                            REAL(nuggets_all_ord), REAL(nuggets_ord), n, 1, REAL(out), &nfail, &first);
+                            resident ? NULL : REAL(nuggets_all_ord), resident ? NULL : REAL(nuggets_ord), n, 1,
+                            REAL(out), &nfail, &first);
   if (st != GPV_OK) { UNPROTECT(1); check(st); }
   warn_fail(nfail, first);
   UNPROTECT(1);
@@ -201,14 +205,18 @@ SEXP gpvb200_csc_pattern(SEXP ptr) {
 /* ... and @x per createU call: kernel + createU.R:158-160 + the triplet sort of sparseMatrix (:161) */
 SEXP gpvb200_U_values_csc(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_ord, SEXP nuggets_ord) {
   const int multi = is_multi(ptr);
+  const int resident = Rf_isNull(nuggets_all_ord) && Rf_isNull(nuggets_ord);   /* see gpvb200_U_values */
+  if (resident && multi) Rf_error("resident scalar nugget: single-device handle only");
+  const int64_t n = resident ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(nuggets_ord);
   int64_t nnz = 0, nfail = 0, first = -1;
   check(multi ? gpv_multi_csc_dims(get_multi(ptr), NULL, &nnz, NULL) : gpv_csc_dims(get_handle(ptr), NULL, &nnz, NULL));
   SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
   gpv_status st = multi
       ? gpv_multi_u_values_csc(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                               REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first)
+                               REAL(nuggets_all_ord), REAL(nuggets_ord), n, REAL(out), &nfail, &first)
       : gpv_u_values_csc(get_handle(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
-                         REAL(nuggets_all_ord), REAL(nuggets_ord), XLENGTH(nuggets_ord), REAL(out), &nfail, &first);
+                         resident ? NULL : REAL(nuggets_all_ord), resident ? NULL : REAL(nuggets_ord), n, REAL(out),
+                         &nfail, &first);
   if (st != GPV_OK) { UNPROTECT(1); check(st); }
   warn_fail(nfail, first);
   UNPROTECT(1);
@@ -230,7 +238,7 @@ SEXP gpvb200_U_sparsity(SEXP ptr) {
   return out;
 }
 
-/* scalar nugget built on the device; afterwards the likelihood calls may pass NULL (R: NULL) vectors */
+/* scalar nugget built on the device; afterwards the likelihood and U-values calls may pass NULL (R: NULL) vectors */
 SEXP gpvb200_set_scalar_nugget(SEXP ptr, SEXP nugget) {
   if (is_multi(ptr)) Rf_error("resident scalar nugget: single-device handle only");
   check(gpv_set_scalar_nugget(get_handle(ptr), Rf_asReal(nugget)));

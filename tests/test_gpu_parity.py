@@ -363,10 +363,25 @@ def test_likelihood_reuses_resident_data_and_scalar_nugget():
                 r1 = h.loglik_z("matern", [1.0, 0.2, 1.5], None, None, None)
                 r2 = h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all / 0.07 * 0.11, tau / 0.07 * 0.11, z)
                 assert abs(r1["loglik"] - r2["loglik"]) <= 1e-12 * abs(r2["loglik"])
-            # a U-values call overwrites the nugget buffer: the next reuse must be refused, not silently wrong
+            # U values with the resident scalar nugget (no per-call nugget upload): the same bits as with the vectors,
+            # and the vectors stay resident for the next call
+            want_p = h.values_packed("matern", [1.0, 0.2, 1.5], nug_all / 0.07 * 0.11, tau / 0.07 * 0.11)
+            h.set_scalar_nugget(0.11)
+            for _ in range(2):
+                got_p = h.values_packed("matern", [1.0, 0.2, 1.5], None, None)
+                assert got_p[1:] == want_p[1:] and np.array_equal(got_p[0], want_p[0])
+            want_c = h.values_csc("matern", [1.0, 0.2, 1.5], nug_all / 0.07 * 0.11, tau / 0.07 * 0.11)
+            h.set_scalar_nugget(0.11)
+            got_c = h.values_csc("matern", [1.0, 0.2, 1.5], None, None)
+            assert np.array_equal(got_c[0], want_c[0])
+            assert h.loglik_numerator("matern", [1.0, 0.2, 1.5], None, None, None, skip_rows=skip) == a
+            # a U-values call that brings nugget vectors overwrites the buffer: the next reuse must be refused, not
+            # silently wrong
             h.values_packed("matern", [1.0, 0.2, 1.5], nug_all, tau)
             with pytest.raises(G.GpvError):
                 h.loglik_numerator("matern", [1.0, 0.2, 1.5], None, None, None, skip_rows=skip)
+            with pytest.raises(G.GpvError):
+                h.values_packed("matern", [1.0, 0.2, 1.5], None, None)
 
 
 def test_zero_nugget_createU_trimming():
