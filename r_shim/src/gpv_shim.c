@@ -5,7 +5,8 @@
  * R vectors in place (INTEGER()/REAL()/LOGICAL()), allocates results with Rf_allocMatrix (owned by
  * R's GC) and calls the C ABI of include/gpvecchia_b200.h.
  *
- * NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no R here (no R.h / Rinternals.h).  The same
+ * There is no R in this repository's image (no R.h / Rinternals.h): the file is type-checked and RUN against a
+ * mock of the R C API (tests/r_api_mock, tests/test_r_shim_mock.py), never inside a real R session.  The same
  * C ABI is exercised by gpvecchia_b200/host.py through ctypes.  Build inside the R package with
  *     PKG_LIBS = -L$(GPV_B200_HOME) -lgpvecchia_b200 -Wl,-rpath,$(GPV_B200_HOME)
  *     PKG_CPPFLAGS = -I$(GPV_B200_HOME)/include

@@ -1,6 +1,7 @@
 /* Minimal DECLARATIONS of the R C API subset that r_shim/src/gpv_shim.c uses, written from the public
  * "Writing R Extensions" manual: enough for `gcc -fsyntax-only` to type-check the shim in an image without
- * R (tests/test_capi_cpu.py).  Nothing here is linked or executed. */
+ * R (tests/test_capi_cpu.py), and -- with the definitions in mock_runtime.c -- to build and RUN it
+ * (tests/test_r_shim_mock.py).  Test infrastructure only. */
 #ifndef GPV_R_API_MOCK_RINTERNALS_H
 #define GPV_R_API_MOCK_RINTERNALS_H
 #include <stddef.h>
