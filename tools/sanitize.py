@@ -29,6 +29,9 @@ for loc, (n, m, d, layout) in [(l, c) for l in ("0", "1") for c in CASES]:
             h.values_csc(ct, cp, nug_all, tau)
             h.loglik_numerator(ct, cp, nug_all, tau, z, skip_rows=n if layout == "zy" else 0)
         h.u_sparsity(); h.csc_pattern()
+        h.set_scalar_nugget(0.1)                       # resident scalar nugget: NULL vectors in the value calls
+        h.values_packed("matern", [1.0, 0.2, 1.5], None, None)
+        h.values_csc("matern", [1.0, 0.2, 1.5], None, None)
         if layout == "z":
             h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all, tau, z)
 G.MaternFun(np.linspace(0, 3, 100), [1.0, 0.3, 1.3])
