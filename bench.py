@@ -562,7 +562,7 @@ class Runner:
             step()
         self.barrier()
         dt = self.allmax(time.perf_counter() - t0)
-        h2d = 8 * (pb["nug_all"].size + n_obs_slice)
+        h2d = 8 * (h.nuggets_read + n_obs_slice)     # what the call copies: the nuggets its rows name + its tau slice
         d2h = 8 * total
         # ceiling: the same number of bytes as plain pinned copies, all ranks at once
         d_src = torch.empty(total, dtype=torch.float64, device=self.dev)
@@ -755,8 +755,9 @@ def main():
     e2e_value = n_sets / em["seconds_per_step"]
     d2h_all = sum_over_ranks(em["d2h"], R)
     e2e = {"value": e2e_value, "unit": "sets/s", "h2d_bytes_per_step": em["h2d"], "d2h_bytes_per_step": em["d2h"],
-           "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers; per rank: all per-location "
-                   "nuggets up, its rows' U values and its slice of Zentries down)",
+           "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers; per rank: the per-location "
+                   "nuggets its rows name up (a prefix for a row shard; staged with the output chunks), its rows' U values "
+                   "and its slice of Zentries down)",
            "achieved_gbs": d2h_all / em["seconds_per_step"] / 1e9,
            "ceiling_gbs": d2h_all / em["copy_seconds_per_step"] / 1e9,
            "frac": em["copy_seconds_per_step"] / em["seconds_per_step"],

@@ -17,7 +17,7 @@ GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
 # every symbol include/gpvecchia_b200.h declares (tests check the .so exports all of them)
 EXPORTED = [
     "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_create", "gpv_create_shard", "gpv_destroy",
-    "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_u_values_packed",
+    "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_nuggets_read", "gpv_u_values_packed",
     "gpv_u_nzentries_mat", "gpv_u_values_packed_mat", "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
     "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
     "gpv_loglik_numerator", "gpv_loglik_z", "gpv_set_scalar_nugget", "gpv_u_dev", "gpv_last_kernel_ms", "gpv_kernel_time_stats", "gpv_last_kernel_name",
@@ -63,6 +63,8 @@ def _load():
     L.gpv_u_nzentries.restype = i32
     L.gpv_packed_len.argtypes = [vp]
     L.gpv_packed_len.restype = i64
+    L.gpv_nuggets_read.argtypes = [vp]
+    L.gpv_nuggets_read.restype = i64
     L.gpv_u_values_packed.argtypes = [vp, cp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i64), C.POINTER(i64)]
     L.gpv_u_values_packed.restype = i32
     L.gpv_csc_dims.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]

@@ -233,6 +233,29 @@ __global__ void gather_percall_kernel(const double* __restrict__ nuggets, const 
   nug_out[i] = nuggets[order[i]];
   if (z_out != nullptr) { const int r = zsrc[i]; z_out[i] = r >= 0 ? zord[r] : 0.0; }
 }
+// largest neighbour id (0-based, -1 = none) named by the rows of each output chunk
+__global__ void chunk_max_id_kernel(const int32_t* __restrict__ nn, int64_t nrows, int p, const int64_t* __restrict__ chunk_row,
+                                    int nc, int* __restrict__ cmax) {
+  __shared__ int smax[32];
+  if (threadIdx.x < 32) smax[threadIdx.x] = -1;
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows) {
+    int m = -1;
+    for (int j = 0; j < p; ++j) { const int v = nn[r * p + j]; m = v > m ? v : m; }
+    int c = 0;
+    while (c + 1 < nc && r >= chunk_row[c + 1]) ++c;
+    atomicMax(&smax[c], m);
+  }
+  __syncthreads();
+  if (threadIdx.x < nc && smax[threadIdx.x] >= 0) atomicMax(&cmax[threadIdx.x], smax[threadIdx.x]);
+}
+// locations [a, b) of the per-call nuggets into replica order (the range form of gather_percall_kernel)
+__global__ void scatter_nuggets_kernel(const double* __restrict__ nuggets, const int32_t* __restrict__ inv, int64_t a, int64_t b,
+                                       double* __restrict__ nug_out) {
+  const int64_t i = a + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b) nug_out[inv[i]] = nuggets[i];
+}
 __global__ void compose_index_kernel(const int32_t* __restrict__ obsrank, const int32_t* __restrict__ order, int64_t N,
                                      int32_t* __restrict__ zsrc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,6 +606,14 @@ struct gpv_handle {
   int64_t chunk_row[kChunks + 1] = {};   // first (shard-local) row of each chunk
   int64_t chunk_csc[kChunks + 1] = {};   // compressed-column offset where each chunk's columns start (ensure_csc)
   cudaEvent_t chunk_done[kChunks] = {};
+  // per-call nugget upload: a set reads only the nuggets of the ids it names, so the handle needs nuggets[0, nug_need)
+  // (nug_need = 1 + the largest id of its rows: a row shard of an ordered layout needs a prefix) and chunk c of the
+  // overlapped call needs [0, chunk_need[c]) -- the upload is pipelined with the chunks (in_stream)
+  int64_t nug_need = 0;
+  int64_t chunk_need[kChunks] = {};
+  cudaStream_t in_stream = nullptr;
+  cudaEvent_t chunk_in[kChunks] = {};
+  int32_t* d_inv = nullptr;           // [Nlocs] locality layer: position of location i in the replica
   static const int kRing = 128;
   cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
   int64_t n_launch = 0, stats_base = 0;
@@ -612,7 +643,10 @@ static void free_handle(gpv_handle* h) {
     if (h->ev_stop[i]) cudaEventDestroy(h->ev_stop[i]);
   }
   for (int i = 0; i < gpv_handle::kChunks; ++i) if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]);
+  for (int i = 0; i < gpv_handle::kChunks; ++i) if (h->chunk_in[i]) cudaEventDestroy(h->chunk_in[i]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->in_stream) cudaStreamDestroy(h->in_stream);
+  cudaFree(h->d_inv);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -736,6 +770,8 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   H_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < gpv_handle::kChunks; ++i) H_TRY(cudaEventCreateWithFlags(&h->chunk_done[i], cudaEventDisableTiming));
+  H_TRY(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < gpv_handle::kChunks; ++i) H_TRY(cudaEventCreateWithFlags(&h->chunk_in[i], cudaEventDisableTiming));
   for (int i = 0; i < gpv_handle::kRing; ++i) {
     H_TRY(cudaEventCreate(&h->ev_start[i]));
     H_TRY(cudaEventCreate(&h->ev_stop[i]));
@@ -763,6 +799,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaMalloc(&h->d_cond, sizeof(uint64_t) * nr));
   H_TRY(cudaMalloc(&h->d_row_off, sizeof(int64_t) * nr));
   H_TRY(cudaMalloc(&h->d_nuggets, sizeof(double) * (size_t)Nlocs));
+  H_TRY(cudaMemsetAsync(h->d_nuggets, 0, sizeof(double) * (size_t)Nlocs, h->stream));   // entries beyond nug_need stay 0
   H_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 4 * (size_t)(h->max_blocks + kTrivBlocks)));
   H_TRY(cudaMalloc(&h->d_flag, sizeof(int)));
   H_TRY(cudaMalloc(&h->d_obs_partials, sizeof(double) * 2 * kObsBlocks));
@@ -930,6 +967,40 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       h->chunk_row[c] = row;
     }
   }
+  // which nuggets do the rows of each chunk name?  (chunk_need / nug_need, see the handle)
+  {
+    const int nc = h->nchunks;
+    h->nug_need = Nlocs;
+    for (int c = 0; c < nc; ++c) h->chunk_need[c] = Nlocs;
+    if (h->nrows > 0) {
+      int* d_cmax = nullptr;
+      int64_t* d_crow = nullptr;
+      int cmax[gpv_handle::kChunks];
+      H_TRY(cudaMalloc(&d_cmax, sizeof(int) * gpv_handle::kChunks));
+      cudaError_t e = cudaMalloc(&d_crow, sizeof(h->chunk_row));
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_cmax, 0xff, sizeof(int) * gpv_handle::kChunks, h->stream);   // -1
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_crow, h->chunk_row, sizeof(h->chunk_row), cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess) {
+        chunk_max_id_kernel<<<grid_for(h->nrows, 256), 256, 0, h->stream>>>(h->d_nn, h->nrows, p, d_crow, nc, d_cmax);
+        g_launches++;
+        e = cudaMemcpyAsync(cmax, d_cmax, sizeof(int) * gpv_handle::kChunks, cudaMemcpyDeviceToHost, h->stream);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(d_cmax); cudaFree(d_crow);
+      H_TRY(e);
+      int64_t need = 0;
+      for (int c = 0; c < nc; ++c) {
+        if ((int64_t)cmax[c] + 1 > need) need = (int64_t)cmax[c] + 1;
+        h->chunk_need[c] = need;
+      }
+      h->nug_need = need;
+      // rows with n0 <= 1 of a split layout are all written by the first launch: no pipelining there
+      if (h->split) for (int c = 0; c < nc; ++c) h->chunk_need[c] = need;
+    } else {
+      h->nug_need = 0;
+      for (int c = 0; c < nc; ++c) h->chunk_need[c] = 0;
+    }
+  }
   // where are this handle's squared neighbour distances?  (general-nu window; a few microseconds per million rows)
   if (h->nrows > 0) {
     unsigned long long* d_hist = nullptr;
@@ -1020,7 +1091,8 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
       }
-      cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(inv); cudaFree(d_box); cudaFree(d_chunks); cudaFree(tmp);
+      cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(d_box); cudaFree(d_chunks); cudaFree(tmp);
+      if (e == cudaSuccess) h->d_inv = inv; else cudaFree(inv);
       if (e == cudaSuccess) {
         cudaFree(h->d_rowmap); cudaFree(h->d_nn_full);
         h->d_rowmap = rowmap2; h->d_nn_full = nn2;
@@ -1051,6 +1123,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
 
 extern "C" void gpv_destroy(gpv_handle* h) { free_handle(h); }
 extern "C" int64_t gpv_packed_len(const gpv_handle* h) { return h ? h->packed_len : 0; }
+extern "C" int64_t gpv_nuggets_read(const gpv_handle* h) { return h ? h->nug_need : 0; }
 extern "C" const char* gpv_last_kernel_name(const gpv_handle* h) { return h ? h->last_kernel : ""; }
 
 extern "C" gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms) {
@@ -1150,7 +1223,7 @@ static gpv_status ensure_table(gpv_handle* h, CovSetup* cs, cudaStream_t st) {
 static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nuggets, double* d_out,
                               int packed, const double* d_zord, int64_t skip_rows, bool want_loglik,
                               cudaStream_t st, int* nblocks_out, int64_t set_begin = 0,
-                              int64_t set_count = -1) {
+                              int64_t set_count = -1, bool replica_ready = false) {
   UParams& q = cs->q;
   const int64_t all_sets = h->split ? h->nfull : h->nrows;
   if (set_count < 0) set_count = all_sets - set_begin;
@@ -1163,7 +1236,7 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.locs = h->locality ? h->d_locs_s : h->d_locs;
   q.nuggets = d_nuggets;
   if (h->locality) {
-    if (set_begin == 0) {               // once per call (the chunks of a call share it)
+    if (set_begin == 0 && !replica_ready) {   // once per call (the chunks of a call share it)
       if (want_loglik && !h->d_zloc) CUDA_TRY(cudaMalloc(&h->d_zloc, sizeof(double) * (size_t)h->Nlocs));
       gather_percall_kernel<<<grid_for(h->Nlocs, 256), 256, 0, st>>>(d_nuggets, h->d_order, d_zord, h->d_zsrc, h->Nlocs,
                                                                      h->d_nug_s, want_loglik ? h->d_zloc : nullptr);
@@ -1318,7 +1391,8 @@ static bool host_buffer_is_pinned(const void* p) {
 // Per-location nuggets of a U-values call: uploaded, or (both vectors NULL) the ones gpv_set_scalar_nugget left on
 // the device -- a scalar nugget then costs no 8-bytes-per-location upload per call (createU.R:70-78 builds the
 // two vectors from the scalar on the host).  Sets the device.
-static gpv_status take_nuggets(gpv_handle* h, const double* nuggets, const double* nuggets_obsord, int64_t n) {
+static gpv_status take_nuggets(gpv_handle* h, const double* nuggets, const double* nuggets_obsord, int64_t n,
+                               bool defer_upload = false) {
   CUDA_TRY(cudaSetDevice(h->device));
   if (!nuggets && !nuggets_obsord) {
     if (!h->nug_resident) return fail(GPV_ERR_ARG, "no nuggets given and none resident on the handle (gpv_set_scalar_nugget)");
@@ -1328,7 +1402,25 @@ static gpv_status take_nuggets(gpv_handle* h, const double* nuggets, const doubl
   if (!nuggets) return fail(GPV_ERR_ARG, "nuggets is null");
   if (n > 0 && !nuggets_obsord) return fail(GPV_ERR_ARG, "nuggets_obsord is null");
   h->nug_resident = false;             // d_nuggets / d_tau are shared with the likelihood calls
-  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+  if (!defer_upload && h->nug_need > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->nug_need, cudaMemcpyHostToDevice, h->stream));
+  return GPV_OK;
+}
+// Chunk c of an overlapped call is about to be launched: bring up the nuggets its rows name and that no earlier
+// chunk did (upload stream; for ordered layouts chunk c names locations below its last row), into replica order
+// where the locality layer is on.  The uploads of later chunks overlap the copies of earlier results: the two
+// directions of the link are independent.
+static gpv_status stage_chunk_nuggets(gpv_handle* h, const double* nuggets, int c) {
+  const int64_t a = c > 0 ? h->chunk_need[c - 1] : 0, b = h->chunk_need[c];
+  if (b <= a) return GPV_OK;
+  CUDA_TRY(cudaMemcpyAsync(h->d_nuggets + a, nuggets + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, h->in_stream));
+  CUDA_TRY(cudaEventRecord(h->chunk_in[c], h->in_stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->chunk_in[c], 0));
+  if (h->locality) {
+    scatter_nuggets_kernel<<<grid_for(b - a, 256), 256, 0, h->stream>>>(h->d_nuggets, h->d_inv, a, b, h->d_nug_s);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   return GPV_OK;
 }
 // shared body of gpv_u_nzentries / gpv_u_values_packed
@@ -1337,21 +1429,22 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
                                 int packed, int ztail, double* out, double* zout, int64_t* nfail,
                                 int64_t* first_fail) {
   if (!h || !out) return fail(GPV_ERR_ARG, "null argument");
-  gpv_status s = take_nuggets(h, nuggets, nuggets_obsord, n); if (s) return s;
+  const bool chunked = h->nrows > 0 && packed && h->nchunks > 1 && host_buffer_is_pinned(out);
+  const bool staged = chunked && nuggets != nullptr;      // nuggets go up chunk by chunk, too
+  gpv_status s = take_nuggets(h, nuggets, nuggets_obsord, n, staged); if (s) return s;
   CovSetup cs;
   s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
   const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
-  bool chunked = false;
-  if (h->nrows > 0 && packed && h->nchunks > 1 && host_buffer_is_pinned(out)) {
+  if (chunked) {
     // overlapped pipeline: kernel of chunk c+1 (compute stream) runs while the packed values of
     // chunk c travel to the host (copy stream).  The rows of a chunk are contiguous in the packed
     // vector; the n0 <= 1 rows interleaved with them are written by the first launch.
-    chunked = true;
     for (int c = 0; c < h->nchunks; ++c) {
+      if (staged) { s = stage_chunk_nuggets(h, nuggets, c); if (s) return s; }
       s = launch_sets(h, &cs, h->d_nuggets, h->d_out, 1, nullptr, 0, false, h->stream, nullptr,
-                      h->chunk_set[c], h->chunk_set[c + 1] - h->chunk_set[c]);
+                      h->chunk_set[c], h->chunk_set[c + 1] - h->chunk_set[c], staged);
       if (s) return s;
       CUDA_TRY(cudaEventRecord(h->chunk_done[c], h->stream));
       CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
@@ -1428,7 +1521,8 @@ static gpv_status loglik_common(gpv_handle* h, const char* covType, const double
   s = ensure(&h->d_zord, (size_t)n); if (s) return s;
   if (nuggets) {
     h->nug_resident = false;
-    CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->Nlocs, cudaMemcpyHostToDevice, h->stream));
+    if (h->nug_need > 0)
+      CUDA_TRY(cudaMemcpyAsync(h->d_nuggets, nuggets, sizeof(double) * (size_t)h->nug_need, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_tau, nuggets_obsord, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     h->nug_resident = true;
   }

@@ -105,6 +105,7 @@ class UHandle:
                              self.device))
         self._h = h
         self.packed_len = int(lib.gpv_packed_len(h))
+        self.nuggets_read = int(lib.gpv_nuggets_read(h))    # leading entries of `nuggets` a call uploads
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):

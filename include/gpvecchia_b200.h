@@ -88,7 +88,11 @@ gpv_status gpv_set_revcond(gpv_handle* h, const void* revCondOnLatent, gpv_cond_
  * revNNarray ids: 1-based; 0, NA_integer_ and any non-positive value are "missing"; an id > Nlocs makes
  * gpv_create fail with GPV_ERR_ARG.
  * Host output buffers: page-locked memory gets the overlapped (chunked) copy pipeline, pageable memory one
- * launch and one copy. */
+ * launch and one copy.
+ * Of `nuggets` a call reads entries [0, gpv_nuggets_read(h)): one past the largest id the handle's rows name
+ * (all Nlocs for a whole-range handle; a prefix for a row shard of an ordered layout), and that is all it
+ * uploads.  In the chunked pipeline the upload is staged with the chunks (chunk c brings up what its rows name
+ * and no earlier chunk did), so that it overlaps the copies of earlier results. */
 gpv_status gpv_u_nzentries(gpv_handle* h, const char* covType, const double* covparms, int ncovparms,
                            const double* nuggets, const double* nuggets_obsord, int64_t n,
                            double* Lentries, double* Zentries, int64_t* nfail, int64_t* first_fail);
@@ -97,6 +101,7 @@ gpv_status gpv_u_nzentries(gpv_handle* h, const char* covType, const double* cov
  * shard its n0 values (farthest neighbour first, self last), rows concatenated; if Zentries_tail
  * != 0 the 2n Z values follow.  out must hold gpv_packed_len(h) (+2n) doubles. */
 int64_t gpv_packed_len(const gpv_handle* h);
+int64_t gpv_nuggets_read(const gpv_handle* h);
 gpv_status gpv_u_values_packed(gpv_handle* h, const char* covType, const double* covparms,
                                int ncovparms, const double* nuggets, const double* nuggets_obsord,
                                int64_t n, int zentries_tail, double* out, int64_t* nfail,

@@ -19,6 +19,20 @@ VAL_TOL = 1e-10
 LL_TOL = 1e-8
 
 
+def _pinned(n, src=None):
+    """Page-locked float64 host array (numpy view of a pinned torch tensor): what the chunked copy pipeline needs."""
+    import torch
+    t = torch.empty(int(n), dtype=torch.float64).pin_memory()
+    a = t.numpy()
+    if src is not None:
+        a[:] = src
+    _PINNED_KEEPALIVE.append(t)
+    return a
+
+
+_PINNED_KEEPALIVE = []
+
+
 def _rc_double(revCond):
     rc = revCond.astype(np.float64)
     rc[revCond < 0] = np.nan
@@ -606,9 +620,17 @@ def test_chunked_packed_pipeline_matches_single_launch(layout):
     cp = [1.0, H.default_range(n, 2), 1.5]
     with G.UHandle(locs2, revNN, revCond, obs=obs) as h:
         r = h.U_NZentries("matern", cp, nug_all, tau)
-        packed, nf, _ = h.values_packed("matern", cp, nug_all, tau)
+        packed, nf, _ = h.values_packed("matern", cp, nug_all, tau)          # pageable destination: one launch, one copy
+        out = _pinned(packed.size)                                           # page-locked: the chunked pipeline, with the
+        out[:] = np.nan                                                      # nugget upload staged chunk by chunk
+        packed2, nf2, _ = h.values_packed("matern", cp, nug_all, tau, out=out)
+        _, nnz, _ = h.csc_dims()
+        x1, _, _ = h.values_csc("matern", cp, nug_all, tau)
+        x2, _, _ = h.values_csc("matern", cp, _pinned(nug_all.size, nug_all), tau, out=_pinned(nnz))
     want = np.concatenate([r["Lentries"].ravel()[(revNN[:, ::-1] != 0).ravel()], r["Zentries"]])
     assert nf == 0 and np.array_equal(packed, want)
+    assert nf2 == 0 and np.array_equal(packed2, want)
+    assert np.array_equal(x1, x2)
     # and against the oracle on a sample of rows
     rows = np.r_[0:50, n - 50:n] if layout == "z" else np.r_[n:n + 50, 2 * n - 50:2 * n]
     rc = revCond.astype(np.float64); rc[revCond < 0] = np.nan
@@ -618,6 +640,44 @@ def test_chunked_packed_pipeline_matches_single_launch(layout):
         ref = pr.Lentries()
         scale = np.abs(ref).max(axis=1, keepdims=True)
         assert (np.abs(r["Lentries"][a:b] - ref) / scale).max() < 1e-9
+
+
+@pytest.mark.parametrize("locality", ["0", "1"])
+def test_chunked_pipeline_with_neighbour_ids_in_any_order(locality, monkeypatch):
+    # U_NZentries does not ask for an ordered layout: a row may name ANY location, also later ones.  The staged
+    # nugget upload of the chunked call (chunk c brings up what its rows name) must then degrade to "everything
+    # before the first chunk", not read nuggets that have not arrived.  Also a row shard, which needs a prefix only.
+    monkeypatch.setenv("GPV_LOCALITY", locality)
+    n, m = 140000, 6
+    rng = np.random.default_rng(11)
+    locs = H.make_locs(n, 2, stream=96)
+    revNN = H.rev(H.ordered_nn_kdtree(locs, m)).astype(np.int64).copy()       # ordered neighbours, self last ...
+    far = rng.integers(0, n, size=n // 50)                                    # ... and in 2 % of the rows a later one
+    tgt = np.minimum(far + rng.integers(1, n // 2, size=far.size), n - 1)
+    ok = (revNN[far] != (tgt + 1)[:, None]).all(axis=1) & (revNN[far, 0] != 0)
+    revNN[far[ok], 0] = tgt[ok] + 1
+    revCond = np.zeros_like(revNN, dtype=np.int32)
+    nug = H.make_nuggets(n, stream=96)
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    rc = revCond.astype(np.float64)
+    for a, b in ((0, n), (n // 3, n // 3 + 66000)):
+        with G.UHandle(locs, revNN, revCond, obs=np.ones(n, dtype=bool), row_begin=a, row_end=b) as h:
+            ztail = (a, b) == (0, n)
+            assert h.nuggets_read == revNN[a:b].max()             # one past the largest (0-based) id its rows name
+            want, nf, _ = h.values_packed("matern", cp, nug, nug, zentries_tail=ztail)
+            out = _pinned(want.size)
+            out[:] = np.nan
+            got, nf2, _ = h.values_packed("matern", cp, nug, nug, zentries_tail=ztail, out=out)
+        assert nf == nf2 == 0 and np.array_equal(got, want)
+        rows = np.r_[a:a + 40, b - 40:b]
+        pr = O.RowsProblem(locs, revNN[rows], rc[rows], 0, nug, "matern", np.array(cp))
+        pr.run(2)
+        ref = pr.Lentries()
+        n0 = (revNN[a:b] != 0).sum(axis=1)
+        off = np.concatenate([[0], np.cumsum(n0)])
+        for k, r_ in enumerate(rows):
+            v = got[off[r_ - a]:off[r_ - a + 1]]
+            assert np.abs(v - ref[k, :v.size]).max() <= VAL_TOL * np.abs(ref[k]).max()
 
 
 def test_whole_loglik_on_gpu_for_pure_z_conditioning():
