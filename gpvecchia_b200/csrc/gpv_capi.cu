@@ -1230,8 +1230,12 @@ static gpv_status launch_sets(gpv_handle* h, CovSetup* cs, const double* d_nugge
   q.nrows = h->nrows; q.row0 = h->row_begin; q.p = h->p; q.d = h->d;
   q.nsets = set_count;
   q.set_base = set_begin;
-  // whole-range launches of a handle with the locality layer run in one global Morton order
-  const bool global_order = h->d_rowmap_g != nullptr && set_begin == 0 && set_count == all_sets;
+  // whole-range launches of a handle with the locality layer run in one global Morton order -- the closed forms
+  // only: the general-nu kernel reads its coefficient table by distance interval, and a warp whose four sets come
+  // from rows of very different rank (neighbourhoods of very different size, which a purely spatial order puts side
+  // by side) hits more distinct intervals per load.  In the chunk-major order (16 bands of the row index, Morton
+  // inside) it is 6 % faster at n = 1e6 and 5 % at n = 1e7 (profiles/r02_bench_n1.json against the global order).
+  const bool global_order = h->d_rowmap_g != nullptr && set_begin == 0 && set_count == all_sets && q.cov != COV_GENERAL;
   q.rowmap = h->mapped ? (global_order ? h->d_rowmap_g : h->d_rowmap + set_begin) : nullptr;
   q.locs = h->locality ? h->d_locs_s : h->d_locs;
   q.nuggets = d_nuggets;
