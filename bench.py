@@ -758,6 +758,9 @@ def main():
            "call": "gpv_u_values_packed (createU's U_NZentries + packing, pinned host buffers; per rank: the per-location "
                    "nuggets its rows name up (a prefix for a row shard; staged with the output chunks), its rows' U values "
                    "and its slice of Zentries down)",
+           "bytes_per_step_all_ranks": {"h2d": sum_over_ranks(em["h2d"], R), "d2h": d2h_all,
+                                        "what": "h2d/d2h_bytes_per_step above are rank 0's; a later rank of an ordered "
+                                                "layout uploads a longer prefix of the nuggets"},
            "achieved_gbs": d2h_all / em["seconds_per_step"] / 1e9,
            "ceiling_gbs": d2h_all / em["copy_seconds_per_step"] / 1e9,
            "frac": em["copy_seconds_per_step"] / em["seconds_per_step"],
