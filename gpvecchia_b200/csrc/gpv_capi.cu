@@ -21,6 +21,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cub/cub.cuh>
 
@@ -614,6 +615,14 @@ struct gpv_handle {
   cudaStream_t in_stream = nullptr;
   cudaEvent_t chunk_in[kChunks] = {};
   int32_t* d_inv = nullptr;           // [Nlocs] locality layer: position of location i in the replica
+  // results into PAGEABLE host memory (every R vector): worker threads, each with a page-locked slot and a stream,
+  // fetch pieces from the device and copy them into the caller's buffer (pageable_copy)
+  static const int kCopyWorkers = 8;
+  static const size_t kCopyPiece = (size_t)4 << 20;
+  cudaStream_t wstream[kCopyWorkers] = {};
+  void* wslot[kCopyWorkers] = {};
+  cudaEvent_t ready_ev = nullptr;     // "everything launched so far on the compute stream is done"
+  int copy_workers_cap = kCopyWorkers;
   static const int kRing = 128;
   cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
   int64_t n_launch = 0, stats_base = 0;
@@ -646,6 +655,11 @@ static void free_handle(gpv_handle* h) {
   for (int i = 0; i < gpv_handle::kChunks; ++i) if (h->chunk_in[i]) cudaEventDestroy(h->chunk_in[i]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->in_stream) cudaStreamDestroy(h->in_stream);
+  for (int i = 0; i < gpv_handle::kCopyWorkers; ++i) {
+    if (h->wstream[i]) cudaStreamDestroy(h->wstream[i]);
+    if (h->wslot[i]) cudaFreeHost(h->wslot[i]);
+  }
+  if (h->ready_ev) cudaEventDestroy(h->ready_ev);
   cudaFree(h->d_inv);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -771,6 +785,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < gpv_handle::kChunks; ++i) H_TRY(cudaEventCreateWithFlags(&h->chunk_done[i], cudaEventDisableTiming));
   H_TRY(cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+  H_TRY(cudaEventCreateWithFlags(&h->ready_ev, cudaEventDisableTiming));
   for (int i = 0; i < gpv_handle::kChunks; ++i) H_TRY(cudaEventCreateWithFlags(&h->chunk_in[i], cudaEventDisableTiming));
   for (int i = 0; i < gpv_handle::kRing; ++i) {
     H_TRY(cudaEventCreate(&h->ev_start[i]));
@@ -1124,6 +1139,9 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
 extern "C" void gpv_destroy(gpv_handle* h) { free_handle(h); }
 extern "C" int64_t gpv_packed_len(const gpv_handle* h) { return h ? h->packed_len : 0; }
 extern "C" int64_t gpv_nuggets_read(const gpv_handle* h) { return h ? h->nug_need : 0; }
+extern "C" void gpv_internal_set_copy_workers(gpv_handle* h, int n) {
+  if (h) h->copy_workers_cap = n < 1 ? 1 : (n > gpv_handle::kCopyWorkers ? gpv_handle::kCopyWorkers : n);
+}
 extern "C" const char* gpv_last_kernel_name(const gpv_handle* h) { return h ? h->last_kernel : ""; }
 
 extern "C" gpv_status gpv_last_kernel_ms(gpv_handle* h, float* ms) {
@@ -1383,6 +1401,56 @@ extern "C" gpv_status gpv_u_dev(gpv_handle* h, const char* covType, const double
   return GPV_OK;
 }
 
+// ---- device results into pageable host memory -------------------------------------------------------------------
+// cudaMemcpy into pageable memory goes through the driver's own staging buffer on ONE thread: 16 GB/s into a buffer
+// that has been touched before, 4.4 GB/s into fresh pages (what Rf_allocVector hands out: every 4 KB page faults on
+// its first write) -- 60 ms for the 264 MB of U at n = 1e6 against 5 ms into page-locked memory.  Here up to 8 worker
+// threads each fetch a 4 MB piece into a page-locked slot of their own (own stream) and copy it into the caller's
+// buffer: the page faults and the host copies run in parallel, the link stays busy.  A piece is fetched once the
+// event of the launch that produces it has fired (all events are recorded before the workers start).  The workers
+// touch nothing but the two buffers: no R API, no handle state.
+struct CopyPiece { const char* src; char* dst; size_t bytes; cudaEvent_t ready; };
+static void add_copy_pieces(std::vector<CopyPiece>* v, const void* src, void* dst, size_t bytes, cudaEvent_t ready) {
+  for (size_t o = 0; o < bytes; o += gpv_handle::kCopyPiece) {
+    const size_t b = bytes - o < gpv_handle::kCopyPiece ? bytes - o : gpv_handle::kCopyPiece;
+    v->push_back({(const char*)src + o, (char*)dst + o, b, ready});
+  }
+}
+static gpv_status pageable_copy(gpv_handle* h, const std::vector<CopyPiece>& pieces) {
+  if (pieces.empty()) return GPV_OK;
+  unsigned hc = std::thread::hardware_concurrency();
+  int nw = (int)(hc ? (hc + 1) / 2 : 4);
+  if (nw > h->copy_workers_cap) nw = h->copy_workers_cap;
+  if (nw > (int)pieces.size()) nw = (int)pieces.size();
+  if (nw < 1) nw = 1;
+  for (int w = 0; w < nw; ++w) {
+    if (!h->wstream[w]) CUDA_TRY(cudaStreamCreateWithFlags(&h->wstream[w], cudaStreamNonBlocking));
+    if (!h->wslot[w]) CUDA_TRY(cudaHostAlloc(&h->wslot[w], gpv_handle::kCopyPiece, cudaHostAllocDefault));
+  }
+  std::atomic<size_t> next(0);
+  std::atomic<int> err((int)cudaSuccess);
+  auto work = [&](int w) {
+    if (cudaSetDevice(h->device) != cudaSuccess) { err.store((int)cudaErrorInvalidDevice); return; }
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= pieces.size() || err.load() != (int)cudaSuccess) return;
+      const CopyPiece& pc = pieces[i];
+      cudaError_t e = pc.ready ? cudaEventSynchronize(pc.ready) : cudaSuccess;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h->wslot[w], pc.src, pc.bytes, cudaMemcpyDeviceToHost, h->wstream[w]);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->wstream[w]);
+      if (e != cudaSuccess) { err.store((int)e); return; }
+      std::memcpy(pc.dst, h->wslot[w], pc.bytes);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nw; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& t : pool) t.join();
+  CUDA_TRY((cudaError_t)err.load());
+  return GPV_OK;
+}
+static const size_t kPageableThreshold = (size_t)8 << 20;   // below: one cudaMemcpyAsync
+
 // The chunked pipeline overlaps kernel launches with device-to-host copies; that only works into page-locked
 // memory.  Into pageable memory (every R vector, plain numpy arrays) cudaMemcpyAsync blocks the host until the
 // copy is done, so the next chunk's kernel would not even be enqueued: 16 launches and no overlap.  Such
@@ -1433,29 +1501,39 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
                                 int packed, int ztail, double* out, double* zout, int64_t* nfail,
                                 int64_t* first_fail) {
   if (!h || !out) return fail(GPV_ERR_ARG, "null argument");
-  const bool chunked = h->nrows > 0 && packed && h->nchunks > 1 && host_buffer_is_pinned(out);
-  const bool staged = chunked && nuggets != nullptr;      // nuggets go up chunk by chunk, too
+  const size_t full = (size_t)h->nrows * h->p;
+  const size_t out_bytes = sizeof(double) * (packed ? (size_t)h->packed_len : full);
+  const bool pinned = host_buffer_is_pinned(out);
+  // pageable destination of some size: worker threads fetch and copy (pageable_copy); page-locked: the copy stream
+  const bool paged = !pinned && h->nrows > 0 && out_bytes >= kPageableThreshold;
+  const bool chunk_launches = h->nrows > 0 && packed && h->nchunks > 1 && (pinned || paged);
+  const bool chunked = chunk_launches && pinned;
+  const bool staged = chunk_launches && nuggets != nullptr;      // nuggets go up chunk by chunk, too
+  std::vector<CopyPiece> pieces;
   gpv_status s = take_nuggets(h, nuggets, nuggets_obsord, n, staged); if (s) return s;
   CovSetup cs;
   s = setup_cov(covType, covparms, ncov, h->w_max, &cs, h->win_top_exp); if (s) return s;
   s = ensure_table(h, &cs, h->stream); if (s) return s;
-  const size_t full = (size_t)h->nrows * h->p;
   s = ensure(&h->d_out, full); if (s) return s;
-  if (chunked) {
+  if (chunk_launches) {
     // overlapped pipeline: kernel of chunk c+1 (compute stream) runs while the packed values of
-    // chunk c travel to the host (copy stream).  The rows of a chunk are contiguous in the packed
-    // vector; the n0 <= 1 rows interleaved with them are written by the first launch.
+    // chunk c travel to the host (copy stream, or the copy workers).  The rows of a chunk are contiguous in the
+    // packed vector; the n0 <= 1 rows interleaved with them are written by the first launch.
     for (int c = 0; c < h->nchunks; ++c) {
       if (staged) { s = stage_chunk_nuggets(h, nuggets, c); if (s) return s; }
       s = launch_sets(h, &cs, h->d_nuggets, h->d_out, 1, nullptr, 0, false, h->stream, nullptr,
                       h->chunk_set[c], h->chunk_set[c + 1] - h->chunk_set[c], staged);
       if (s) return s;
       CUDA_TRY(cudaEventRecord(h->chunk_done[c], h->stream));
-      CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
       const int64_t o0 = h->chunk_out[c], o1 = h->chunk_out[c + 1];
-      if (o1 > o0)
-        CUDA_TRY(cudaMemcpyAsync(out + o0, h->d_out + o0, sizeof(double) * (size_t)(o1 - o0),
-                                 cudaMemcpyDeviceToHost, h->copy_stream));
+      if (chunked) {
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+        if (o1 > o0)
+          CUDA_TRY(cudaMemcpyAsync(out + o0, h->d_out + o0, sizeof(double) * (size_t)(o1 - o0),
+                                   cudaMemcpyDeviceToHost, h->copy_stream));
+      } else if (o1 > o0) {
+        add_copy_pieces(&pieces, h->d_out + o0, out + o0, sizeof(double) * (size_t)(o1 - o0), h->chunk_done[c]);
+      }
     }
   } else if (h->nrows > 0) {
     s = launch_sets(h, &cs, h->d_nuggets, h->d_out, packed, nullptr, 0, false, h->stream, nullptr);
@@ -1466,12 +1544,8 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
   }
   const bool want_z = (n > 0) && (zout != nullptr || ztail);
   if (want_z) { s = run_zentries(h, nuggets_obsord, n); if (s) return s; }
-  if (packed) {
-    if (h->packed_len > 0 && !chunked)
-      CUDA_TRY(cudaMemcpyAsync(out, h->d_out, sizeof(double) * (size_t)h->packed_len, cudaMemcpyDeviceToHost, h->stream));
-    if (ztail && n > 0)
-      CUDA_TRY(cudaMemcpyAsync(out + h->packed_len, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-  } else if (h->nrows > 0) {
+  const double* d_src = h->d_out;
+  if (!packed && h->nrows > 0) {
     if (h->out2_doubles < full) {
       cudaFree(h->d_out2); h->d_out2 = nullptr; h->out2_doubles = 0;
       CUDA_TRY(cudaMalloc(&h->d_out2, sizeof(double) * full));
@@ -1481,10 +1555,20 @@ static gpv_status u_host_common(gpv_handle* h, const char* covType, const double
     transpose_rm_to_cm_kernel<<<grid, block, 0, h->stream>>>(h->d_out, h->nrows, h->p, h->d_out2);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out, h->d_out2, sizeof(double) * full, cudaMemcpyDeviceToHost, h->stream));
+    d_src = h->d_out2;
   }
-  if (!packed && zout && n > 0)
-    CUDA_TRY(cudaMemcpyAsync(zout, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  double* z_dst = packed ? (ztail ? out + h->packed_len : nullptr) : zout;
+  if (paged) {
+    CUDA_TRY(cudaEventRecord(h->ready_ev, h->stream));      // everything launched above
+    if (!chunk_launches) add_copy_pieces(&pieces, d_src, out, out_bytes, h->ready_ev);
+    if (z_dst && n > 0) add_copy_pieces(&pieces, h->d_zent, z_dst, sizeof(double) * 2 * (size_t)n, h->ready_ev);
+    s = pageable_copy(h, pieces); if (s) return s;
+  } else {
+    if (!chunked && out_bytes > 0 && h->nrows > 0)
+      CUDA_TRY(cudaMemcpyAsync(out, d_src, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (z_dst && n > 0)
+      CUDA_TRY(cudaMemcpyAsync(z_dst, h->d_zent, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  }
   if (chunked) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
   return read_fail_info(h, nfail, first_fail);
 }

@@ -4,6 +4,11 @@
 #include <cuda_runtime.h>
 #include "u_kernels.cuh"
 
+struct gpv_handle;
+// Upper bound on the copy workers of one handle (results into pageable memory, gpv_capi.cu: pageable_copy); the
+// multi-device front end divides the host's threads between its handles.
+extern "C" void gpv_internal_set_copy_workers(gpv_handle* h, int n);
+
 namespace gpv {
 
 // One entry per compiled instantiation of u_sets_kernel<G,P,D>.

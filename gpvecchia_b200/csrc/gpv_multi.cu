@@ -8,6 +8,7 @@
 // here; the multi-process form (bench.py under torchrun) combines the same partial sums with one
 // all-reduce.
 #include "../../include/gpvecchia_b200.h"
+extern "C" void gpv_internal_set_copy_workers(gpv_handle* h, int n);   // gpv_capi.cu
 
 #include <cmath>
 #include <cstdio>
@@ -94,6 +95,12 @@ extern "C" gpv_status gpv_multi_create(gpv_multi** out, int64_t Nlocs, int p, in
   }
   m->off.assign(ndev + 1, 0);
   for (int i = 0; i < ndev; ++i) m->off[i + 1] = m->off[i] + gpv_packed_len(m->h[i]);
+  {
+    // results into pageable memory: the handles' copy workers share the host's threads
+    const unsigned hc = std::thread::hardware_concurrency();
+    const int per = (int)((hc ? hc : 8u) / (2u * (unsigned)ndev));
+    for (int i = 0; i < ndev; ++i) gpv_internal_set_copy_workers(m->h[i], per < 2 ? 2 : per);
+  }
   if (obs) for (int64_t i = 0; i < Nlocs; ++i) m->n_obs += (obs[i] != 0 && obs[i] != INT32_MIN);
   // one NCCL communicator over the devices (distinct ordinals, no empty shard): optional, the host path stays
   bool distinct = ndev > 1 && m->n_obs > 0;

@@ -87,8 +87,12 @@ gpv_status gpv_set_revcond(gpv_handle* h, const void* revCondOnLatent, gpv_cond_
  * (elementwise, U_NZentries.cpp:110-115): the ranks of a sharded run each move only their slice.
  * revNNarray ids: 1-based; 0, NA_integer_ and any non-positive value are "missing"; an id > Nlocs makes
  * gpv_create fail with GPV_ERR_ARG.
- * Host output buffers: page-locked memory gets the overlapped (chunked) copy pipeline, pageable memory one
- * launch and one copy.
+ * Host output buffers: page-locked memory gets the overlapped (chunked) copy pipeline on a copy stream.  Pageable
+ * memory (every R vector) of 8 MB or more gets the same chunked launches, and up to 8 worker threads of the
+ * library fetch 4 MB pieces into page-locked slots and copy them into the caller's buffer, so that the page
+ * faults of a freshly allocated vector and the host copies run in parallel (n = 1e6, m = 30: 13 ms instead of
+ * the 60 ms of one cudaMemcpy into fresh pages; 5 ms page-locked).  The workers touch the two buffers only.
+ * Smaller pageable outputs: one launch and one copy.
  * Of `nuggets` a call reads entries [0, gpv_nuggets_read(h)): one past the largest id the handle's rows name
  * (all Nlocs for a whole-range handle; a prefix for a row shard of an ordered layout), and that is all it
  * uploads.  In the chunked pipeline the upload is staged with the chunks (chunk c brings up what its rows name

@@ -680,6 +680,44 @@ def test_chunked_pipeline_with_neighbour_ids_in_any_order(locality, monkeypatch)
             assert np.abs(v - ref[k, :v.size]).max() <= VAL_TOL * np.abs(ref[k]).max()
 
 
+@pytest.mark.parametrize("layout", ["z", "zy"])
+def test_results_into_pageable_memory_go_through_the_copy_workers(layout):
+    # every R vector is pageable: outputs of 8 MB or more are fetched in 4 MB pieces by worker threads of the
+    # library (page-locked slots, then memcpy into the caller's buffer).  Same bits as the page-locked route, for
+    # the packed vector with its Z tail, the compressed-column values and the N x p matrix of the stateless call.
+    n, m = 150000, 10
+    locs = H.make_locs(n, 2, stream=95)
+    if layout == "zy":
+        locs2, NN, Cond, obs = H.layout_zy(locs, m, n)
+        nug_all = np.concatenate([H.make_nuggets(n, stream=95), np.zeros(n)])
+    else:
+        locs2, NN = locs, H.ordered_nn_kdtree(locs, m)
+        Cond, obs = H.layout_yz(NN, "z"), np.ones(n, dtype=bool)
+        nug_all = H.make_nuggets(n, stream=95)
+    revNN, revCond = H.rev(NN), H.rev(Cond)
+    tau = nug_all[:n]
+    cp = [1.0, H.default_range(n, 2), 1.5]
+    with G.UHandle(locs2, revNN, revCond, obs=obs) as h:
+        total = h.packed_len + 2 * n
+        assert total * 8 >= (8 << 20)
+        want, nf, _ = h.values_packed("matern", cp, nug_all, tau, out=_pinned(total))
+        got = np.full(total, np.nan)
+        _, nf2, _ = h.values_packed("matern", cp, nug_all, tau, out=got)
+        assert nf == nf2 == 0 and np.array_equal(got, want)
+        got_nz = np.full(h.packed_len, np.nan)                                # no Z tail
+        h.values_packed("matern", cp, nug_all, tau, zentries_tail=False, out=got_nz)
+        assert np.array_equal(got_nz, want[:h.packed_len])
+        _, nnz, _ = h.csc_dims()
+        xw, _, _ = h.values_csc("matern", cp, nug_all, tau, out=_pinned(nnz))
+        xg = np.full(nnz, np.nan)
+        h.values_csc("matern", cp, nug_all, tau, out=xg)
+        assert np.array_equal(xg, xw)
+        r = h.U_NZentries("matern", cp, nug_all, tau)                         # row-major -> column-major -> workers
+        keep = (revNN[:, ::-1] != 0)
+        assert np.array_equal(np.concatenate([r["Lentries"][keep], r["Zentries"]]), want)
+        assert not np.any(r["Lentries"][~keep])
+
+
 def test_whole_loglik_on_gpu_for_pure_z_conditioning():
     # standard Vecchia: denominator terms are per-row closed forms (gpv_loglik_z)
     n, m = 3000, 20
