@@ -12,6 +12,7 @@
 #include "cov_setup.h"
 
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -767,6 +768,15 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   h->entry = entry;
   h->entry_gen = entry_gen;
   h->shard_arrays = shard_arrays;
+  const bool trace = std::getenv("GPV_TRACE_CREATE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!trace) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gpv_create] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
 #define H_TRY(expr)                                                                                 \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
@@ -808,6 +818,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     if (h->max_blocks_gen > h->max_blocks) h->max_blocks = h->max_blocks_gen;   // sizes d_partials
   }
 
+  tick("streams, events, attributes");
   const size_t nr = (size_t)(h->nrows > 0 ? h->nrows : 1);
   H_TRY(cudaMalloc(&h->d_locs, sizeof(double) * (size_t)Nlocs * d));
   H_TRY(cudaMalloc(&h->d_nn, sizeof(int32_t) * nr * p));
@@ -822,6 +833,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
   H_TRY(cudaMalloc(&h->d_nfail, sizeof(unsigned long long)));
   H_TRY(cudaMalloc(&h->d_first_fail, sizeof(long long)));
 
+  tick("fixed allocations");
   // locs: upload column-major, transpose on device; bounding box on the host copy (once)
   double box[6] = {0, 0, 0, 0, 0, 0};   // {min, 1 / extent} of the first three coordinates (locality keys)
   {
@@ -845,6 +857,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     }
     h->w_max = w;
   }
+  tick("locs + bounding box");
   // neighbour ids: upload column-major, transpose + rebase on device, packed offsets by scan
   if (h->nrows > 0) {
     int32_t* tmp = nullptr;
@@ -960,6 +973,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
     h->n_obs = (int64_t)last_e + last_f;
     h->have_obs = true;
   }
+  tick("ids, classes, obs");
   // chunk table for the overlapped packed-output call: sets are in increasing row order, so chunk c
   // owns the packed values of rows [first row of chunk c, first row of chunk c+1)
   {
@@ -982,6 +996,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       h->chunk_row[c] = row;
     }
   }
+  tick("chunk table");
   // which nuggets do the rows of each chunk name?  (chunk_need / nug_need, see the handle)
   {
     const int nc = h->nchunks;
@@ -1016,6 +1031,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       for (int c = 0; c < nc; ++c) h->chunk_need[c] = 0;
     }
   }
+  tick("chunk needs");
   // where are this handle's squared neighbour distances?  (general-nu window; a few microseconds per million rows)
   if (h->nrows > 0) {
     unsigned long long* d_hist = nullptr;
@@ -1041,6 +1057,7 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       h->win_top_exp = med + GPV_TAB_WIN_TOP;
     }
   }
+  tick("distance histogram");
   // locality layer: on for large N (per-location data beyond ~48 MB no longer sit in the L2 next to the streams);
   // GPV_LOCALITY=1 / 0 forces it on / off (tests run both ways on small problems)
   {
@@ -1128,9 +1145,11 @@ static gpv_status create_impl(gpv_handle** out, int64_t Nlocs, int p, int d, con
       H_TRY(e);
     }
   }
+  tick("locality layer");
   *out = h;
   gpv_status st = gpv_set_revcond(h, revCond, cond_type);
   h->cond_uploaded = true;
+  tick("revCond");
   if (st != GPV_OK) { free_handle(h); *out = nullptr; return st; }
   return GPV_OK;
 #undef H_TRY
