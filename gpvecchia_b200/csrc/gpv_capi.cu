@@ -1462,7 +1462,9 @@ static gpv_status pageable_copy(gpv_handle* h, const std::vector<CopyPiece>& pie
     }
   };
   std::vector<std::thread> pool;
-  for (int w = 1; w < nw; ++w) pool.emplace_back(work, w);
+  for (int w = 1; w < nw; ++w) {
+    try { pool.emplace_back(work, w); } catch (...) { break; }   // no thread to be had: the others share the pieces
+  }
   work(0);
   for (auto& t : pool) t.join();
   CUDA_TRY((cudaError_t)err.load());
