@@ -34,6 +34,26 @@ for loc, (n, m, d, layout) in [(l, c) for l in ("0", "1") for c in CASES]:
         h.values_csc("matern", [1.0, 0.2, 1.5], None, None)
         if layout == "z":
             h.loglik_z("matern", [1.0, 0.2, 1.5], nug_all, tau, z)
+# the chunked output pipelines: page-locked destination (copy stream, nugget upload staged with the chunks) and
+# pageable destination of more than 8 MB (copy workers), locality layer off and on
+import torch
+for loc in ("0", "1"):
+    os.environ["GPV_LOCALITY"] = loc
+    n, m = 100000, 10
+    locs = H.make_locs(n, 2, stream=3)
+    NN = H.rev(H.ordered_nn_gpu(locs, m)).astype(np.int64)
+    Cond = H.layout_yz(NN, "z")
+    nug = np.full(n, 0.1)
+    with G.UHandle(locs, H.rev(NN), H.rev(Cond), obs=np.ones(n, dtype=bool)) as h:
+        total = h.packed_len + 2 * n
+        pinned = torch.empty(total, dtype=torch.float64).pin_memory().numpy()
+        h.values_packed("matern", [1.0, 0.02, 1.5], nug, nug, out=pinned)
+        paged = np.empty(total)
+        h.values_packed("matern", [1.0, 0.02, 1.5], nug, nug, out=paged)
+        assert np.array_equal(pinned, paged)
+        _, nnz, _ = h.csc_dims()
+        h.values_csc("matern", [1.0, 0.02, 1.5], nug, nug, out=np.empty(nnz))
+        h.U_NZentries("matern", [1.0, 0.02, 1.5], nug, nug)
 G.MaternFun(np.linspace(0, 3, 100), [1.0, 0.3, 1.3])
 G.EsqeFun(np.linspace(0, 3, 100), [1.0, 0.3, 0.5, 0.2])
 print("sanitize workload done")
