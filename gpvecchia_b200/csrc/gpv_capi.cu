@@ -618,12 +618,12 @@ struct gpv_handle {
   int32_t* d_inv = nullptr;           // [Nlocs] locality layer: position of location i in the replica
   // results into PAGEABLE host memory (every R vector): worker threads, each with a page-locked slot and a stream,
   // fetch pieces from the device and copy them into the caller's buffer (pageable_copy)
-  static const int kCopyWorkers = 8;
+  static const int kCopyWorkers = 16;
   static const size_t kCopyPiece = (size_t)4 << 20;
   cudaStream_t wstream[kCopyWorkers] = {};
   void* wslot[kCopyWorkers] = {};
   cudaEvent_t ready_ev = nullptr;     // "everything launched so far on the compute stream is done"
-  int copy_workers_cap = kCopyWorkers;
+  int copy_workers_cap = 8;
   static const int kRing = 128;
   cudaEvent_t ev_start[kRing] = {}, ev_stop[kRing] = {};   // one pair per set-kernel launch (ring)
   int64_t n_launch = 0, stats_base = 0;
@@ -1440,6 +1440,7 @@ static gpv_status pageable_copy(gpv_handle* h, const std::vector<CopyPiece>& pie
   unsigned hc = std::thread::hardware_concurrency();
   int nw = (int)(hc ? (hc + 1) / 2 : 4);
   if (nw > h->copy_workers_cap) nw = h->copy_workers_cap;
+  if (const char* env = std::getenv("GPV_COPY_WORKERS")) { const int v = std::atoi(env); if (v >= 1 && v <= gpv_handle::kCopyWorkers) nw = v; }
   if (nw > (int)pieces.size()) nw = (int)pieces.size();
   if (nw < 1) nw = 1;
   for (int w = 0; w < nw; ++w) {

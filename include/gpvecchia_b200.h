@@ -91,7 +91,8 @@ gpv_status gpv_set_revcond(gpv_handle* h, const void* revCondOnLatent, gpv_cond_
  * memory (every R vector) of 8 MB or more gets the same chunked launches, and up to 8 worker threads of the
  * library fetch 4 MB pieces into page-locked slots and copy them into the caller's buffer, so that the page
  * faults of a freshly allocated vector and the host copies run in parallel (n = 1e6, m = 30: 13 ms instead of
- * the 60 ms of one cudaMemcpy into fresh pages; 5 ms page-locked).  The workers touch the two buffers only.
+ * the 60 ms of one cudaMemcpy into fresh pages; 5 ms page-locked).  The workers touch the two buffers only;
+ * GPV_COPY_WORKERS=1..16 overrides their number (default: half the host's hardware threads, at most 8).
  * Smaller pageable outputs: one launch and one copy.
  * Of `nuggets` a call reads entries [0, gpv_nuggets_read(h)): one past the largest id the handle's rows name
  * (all Nlocs for a whole-range handle; a prefix for a row shard of an ordered layout), and that is all it
