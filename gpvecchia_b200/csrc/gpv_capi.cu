@@ -58,6 +58,14 @@ extern "C" int gpv_device_count(void) {
   return n;
 }
 extern "C" int64_t gpv_launch_count(void) { return g_launches.load(); }
+// page-locked host memory for result vectors (the R shim's optional custom allocator): portable, so
+// that any device's copy engine writes into it at full rate
+extern "C" void* gpv_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void gpv_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------------
 // kernel registry

@@ -14,6 +14,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <R_ext/Rallocators.h>
 #include "gpvecchia_b200.h"
 
 static void check(gpv_status st) {
@@ -26,6 +27,48 @@ static void warn_fail(int64_t nfail, int64_t first_fail) {
   if (nfail > 0)
     Rf_warning("Cholesky decomposition failed for %lld conditioning set(s) (first at row %lld); "
                "those rows of U are zero", (long long)nfail, (long long)first_fail + 1);
+}
+
+/* ---- result vectors in page-locked memory (optional: options(GPvecchia.b200.pinned_results = TRUE)) ----------
+ * Every ordinary R vector is pageable, and a fresh one faults in page by page: 13 ms for the 264 MB of U at
+ * n = 1e6 even with the library's copy workers, 5 ms into page-locked memory.  R lets a package supply the storage
+ * of a vector (Rf_allocVector3 + R_allocator_t, R >= 3.1.0): the block comes from gpv_host_alloc and goes back to a
+ * small pool when the garbage collector frees the vector, so that the createU() calls of an estimation loop -- same
+ * size every time -- reuse it and do not pay for pinning 264 MB again (tens of milliseconds).  The pool holds at
+ * most kPinPool blocks; a block that does not fit any more is released. */
+#define kPinPool 4
+static struct { void* p; size_t cap; int used; } pin_pool[kPinPool];
+static void* pin_alloc(R_allocator_t* a, size_t bytes) {
+  (void)a;
+  int best = -1, victim = -1;
+  for (int i = 0; i < kPinPool; ++i) {
+    if (pin_pool[i].used) continue;
+    if (pin_pool[i].p && pin_pool[i].cap >= bytes && (best < 0 || pin_pool[i].cap < pin_pool[best].cap)) best = i;
+    /* where a new block would be remembered: an empty slot, else the smallest idle block */
+    if (victim < 0 || (pin_pool[victim].p && (!pin_pool[i].p || pin_pool[i].cap < pin_pool[victim].cap))) victim = i;
+  }
+  if (best >= 0) { pin_pool[best].used = 1; return pin_pool[best].p; }
+  void* p = gpv_host_alloc(bytes);
+  if (!p) return NULL;                                       /* R reports the allocation failure */
+  if (victim >= 0) {                                         /* remember it for reuse, in place of an idle block */
+    if (pin_pool[victim].p) gpv_host_free(pin_pool[victim].p);
+    pin_pool[victim].p = p; pin_pool[victim].cap = bytes; pin_pool[victim].used = 1;
+  }
+  return p;                                                  /* pool full of blocks in use: freed for good on release */
+}
+static void pin_free(R_allocator_t* a, void* p) {
+  (void)a;
+  for (int i = 0; i < kPinPool; ++i)
+    if (pin_pool[i].p == p) { pin_pool[i].used = 0; return; }
+  gpv_host_free(p);
+}
+static SEXP alloc_result(R_xlen_t n) {
+  SEXP opt = Rf_GetOption1(Rf_install("GPvecchia.b200.pinned_results"));
+  if (opt != R_NilValue && Rf_asInteger(opt) == 1 && n > 0) {
+    R_allocator_t al = {pin_alloc, pin_free, NULL, NULL};    /* R keeps its own copy */
+    return Rf_allocVector3(REALSXP, n, &al);
+  }
+  return Rf_allocVector(REALSXP, n);
 }
 
 static int device_from_option(void) {
@@ -172,7 +215,7 @@ SEXP gpvb200_U_values(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_all_or
   if (resident && multi) Rf_error("resident scalar nugget: single-device handle only");
   const int64_t n = resident ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(nuggets_ord);
   const int64_t len = multi ? gpv_multi_packed_len(get_multi(ptr)) : gpv_packed_len(get_handle(ptr));
-  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(len + 2 * n)));
+  SEXP out = PROTECT(alloc_result((R_xlen_t)(len + 2 * n)));
   int64_t nfail = 0, first = -1;
   gpv_status st = multi
       ? gpv_multi_u_values_packed(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
@@ -211,7 +254,7 @@ SEXP gpvb200_U_values_csc(SEXP ptr, SEXP covType, SEXP covparms, SEXP nuggets_al
   const int64_t n = resident ? (int64_t)Rf_asReal(Rf_getAttrib(ptr, Rf_install("n_obs"))) : XLENGTH(nuggets_ord);
   int64_t nnz = 0, nfail = 0, first = -1;
   check(multi ? gpv_multi_csc_dims(get_multi(ptr), NULL, &nnz, NULL) : gpv_csc_dims(get_handle(ptr), NULL, &nnz, NULL));
-  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+  SEXP out = PROTECT(alloc_result((R_xlen_t)nnz));
   gpv_status st = multi
       ? gpv_multi_u_values_csc(get_multi(ptr), CHAR(STRING_ELT(covType, 0)), REAL(covparms), LENGTH(covparms),
                                REAL(nuggets_all_ord), REAL(nuggets_ord), n, REAL(out), &nfail, &first)

@@ -21,6 +21,7 @@
 #include <string.h>
 #include "Rinternals.h"
 #include "R_ext/Rdynload.h"
+#include "R_ext/Rallocators.h"
 
 #define CHARSXP 9
 #define SYMSXP 1
@@ -35,9 +36,11 @@ struct SEXPREC {
   void* addr;             /* external pointer */
   SEXP tag, prot;
   R_CFinalizer_t fin;
+  R_allocator_t custom;   /* Rf_allocVector3: R's own copy of the allocator ... */
+  void* custom_block;     /* ... and the block it returned (header + data) */
 };
 
-static struct SEXPREC nil_rec = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL, NULL};
+static struct SEXPREC nil_rec = {NILSXP, 0, NULL, NULL, NULL, NULL, NULL, NULL, {NULL, NULL, NULL, NULL}, NULL};
 SEXP R_NilValue = &nil_rec;
 SEXP R_NamesSymbol = NULL;
 int R_NaInt = INT_MIN;
@@ -85,6 +88,24 @@ SEXP Rf_allocVector(SEXPTYPE t, R_xlen_t n) {
     }
     default: fprintf(stderr, "mock R: allocVector type %u not supported\n", t); abort();
   }
+}
+/* vector whose storage comes from a custom allocator: one block for header + data, as R does (the data start some
+ * bytes into the block); mock_release plays the garbage collector */
+#define MOCK_HEADER_BYTES 64
+SEXP Rf_allocVector3(SEXPTYPE t, R_xlen_t n, R_allocator_t* al) {
+  if (!al) return Rf_allocVector(t, n);
+  if (t != REALSXP && t != INTSXP && t != LGLSXP) { fprintf(stderr, "mock R: allocVector3 type %u not supported\n", t); abort(); }
+  const size_t elt = (t == REALSXP) ? sizeof(double) : sizeof(int);
+  SEXP s = new_rec((int)t, n, 1);
+  free(s->data);
+  s->custom = *al;
+  s->custom_block = al->mem_alloc(&s->custom, MOCK_HEADER_BYTES + (size_t)(n > 0 ? n : 1) * elt);
+  if (!s->custom_block) Rf_error("cannot allocate vector of size %.1f Mb", (double)n * elt / 1048576.0);
+  s->data = (char*)s->custom_block + MOCK_HEADER_BYTES;
+  return s;
+}
+void mock_release(SEXP s) {
+  if (s->custom_block) { s->custom.mem_free(&s->custom, s->custom_block); s->custom_block = NULL; s->data = NULL; }
 }
 SEXP Rf_allocMatrix(SEXPTYPE t, int nr, int nc) {
   SEXP s = Rf_allocVector(t, (R_xlen_t)nr * nc);

@@ -53,7 +53,7 @@ class MockR:
                 ("mock_protect_depth", C.c_int, []), ("mock_routine_arity", C.c_int, [C.c_char_p]),
                 ("mock_routine_count", C.c_int, []), ("mock_routine_name", C.c_char_p, [C.c_int]),
                 ("mock_set_option", None, [C.c_char_p, P]), ("mock_run_finalizer", None, [P]), ("mock_null_extptr", None, [P]),
-                ("Rf_nrows", C.c_int, [P]), ("Rf_ncols", C.c_int, [P]), ("Rf_isMatrix", C.c_int, [P]),
+                ("mock_release", None, [P]), ("Rf_nrows", C.c_int, [P]), ("Rf_ncols", C.c_int, [P]), ("Rf_isMatrix", C.c_int, [P]),
                 ("R_init_GPvecchiaB200", None, [P])):
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
@@ -288,6 +288,38 @@ def test_handle_routines_build_the_same_U_as_the_ctypes_front_end(R):
     R.L.mock_run_finalizer(h)                                             # idempotent
     with pytest.raises(RError, match="stale device handle"):
         R.call("_GPvecchia_b200_csc_pattern", h)
+
+
+@pytest.mark.gpu
+def test_result_vectors_in_page_locked_memory_through_a_custom_r_allocator(R):
+    # options(GPvecchia.b200.pinned_results = TRUE): the storage of the result vector comes from gpv_host_alloc through
+    # Rf_allocVector3, goes back to the shim's pool when the vector is collected, and is reused by the next call
+    n, m = 100000, 12
+    va = _problem(n, m, 2, "z", stream=35)
+    cp = [1.0, 0.01, 1.5]
+    locs, nn, rc, _, _ = _r_arrays(R, va)
+    h = R.call("_GPvecchia_b200_create", locs, nn, rc, R.logical(np.ones(n, np.int32)))
+    tau = np.full(n, 0.2)
+    args = (h, R.string("matern"), R.real(cp), R.real(tau), R.real(tau))
+    want = R.numpy(R.call("_GPvecchia_b200_U_values", *args))
+    want_x = R.numpy(R.call("_GPvecchia_b200_U_values_csc", *args))
+    R.option("GPvecchia.b200.pinned_results", R.logical([1]))
+    try:
+        v1 = R.call("_GPvecchia_b200_U_values", *args)
+        p1 = R.L.mock_data(v1)
+        assert np.array_equal(R.numpy(v1), want)
+        v2 = R.call("_GPvecchia_b200_U_values", *args)                    # v1 still alive: a second block
+        assert R.L.mock_data(v2) != p1 and np.array_equal(R.numpy(v2), want)
+        R.L.mock_release(v1)                                              # the garbage collector frees v1 ...
+        v3 = R.call("_GPvecchia_b200_U_values", *args)                    # ... and its block serves the next call
+        assert R.L.mock_data(v3) == p1 and np.array_equal(R.numpy(v3), want)
+        x = R.call("_GPvecchia_b200_U_values_csc", *args)
+        assert np.array_equal(R.numpy(x), want_x)
+        for v in (v2, v3, x):
+            R.L.mock_release(v)
+    finally:
+        R.option("GPvecchia.b200.pinned_results", None)
+    R.L.mock_run_finalizer(h)
 
 
 @pytest.mark.gpu
