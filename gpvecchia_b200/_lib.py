@@ -16,7 +16,7 @@ GPV_COND_RLOGICAL_I32, GPV_COND_F64 = 0, 1
 
 # every symbol include/gpvecchia_b200.h declares (tests check the .so exports all of them)
 EXPORTED = [
-    "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_host_alloc", "gpv_host_free", "gpv_create", "gpv_create_shard", "gpv_destroy",
+    "gpv_last_error", "gpv_version", "gpv_device_count", "gpv_host_alloc", "gpv_host_free", "gpv_release_cached", "gpv_create", "gpv_create_shard", "gpv_destroy",
     "gpv_set_revcond", "gpv_u_nzentries", "gpv_packed_len", "gpv_nuggets_read", "gpv_u_values_packed",
     "gpv_u_nzentries_mat", "gpv_u_values_packed_mat", "gpv_csc_dims", "gpv_u_sparsity", "gpv_u_csc_pattern", "gpv_u_values_csc",
     "gpv_multi_csc_dims", "gpv_multi_u_csc_pattern", "gpv_multi_u_values_csc",
@@ -53,6 +53,8 @@ def _load():
     L.gpv_host_alloc.restype = vp
     L.gpv_host_free.argtypes = [vp]
     L.gpv_host_free.restype = None
+    L.gpv_release_cached.argtypes = []
+    L.gpv_release_cached.restype = None
     L.gpv_create.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, i64, i64, i32]
     L.gpv_create.restype = i32
     L.gpv_create_shard.argtypes = [C.POINTER(vp), i64, i32, i32, vp, vp, vp, i32, vp, i64, i64, i32]

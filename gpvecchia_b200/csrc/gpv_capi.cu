@@ -1717,6 +1717,68 @@ extern "C" gpv_status gpv_loglik_z(gpv_handle* h, const char* covType, const dou
   return GPV_OK;
 }
 
+// ---- the stateless drop-in and its one-handle cache ------------------------------------------------------------
+// U_NZentries(...) takes everything on every call (src/RcppExports.cpp:49-67), but createU calls it up to 300 times
+// per vecchia_specify with the same locsord / revNNarray (R/vecchia_wrappers.R:72-93).  Creating and destroying a
+// handle per call costs ~170 ms at n = 1e6 (uploads, conversions, device allocations and frees) next to ~25 ms of
+// work, so the last handle is kept and recognised by a 64-bit fingerprint of the parameter-free arrays (multi-threaded
+// pass over them: ~10 ms); a call that only brings another revCond (createU.R:83-86, zero nuggets) re-uploads just
+// that.  GPV_STATELESS_CACHE=0 disables it; gpv_release_cached() frees the kept handle (package unload).
+namespace {
+struct StatelessCache {
+  std::mutex mu;
+  gpv_handle* h = nullptr;
+  int64_t Nlocs = 0;
+  int p = 0, d = 0, device = -1, cond_type = -1;
+  uint64_t key_static = 0, key_cond = 0;
+} g_stateless;
+
+uint64_t fingerprint(const void* ptr, size_t bytes) {
+  // 64-bit multiplicative hash of 8-byte words, 1 MB blocks hashed in parallel and combined in order
+  const size_t kBlock = (size_t)1 << 20;
+  const size_t nblocks = (bytes + kBlock - 1) / kBlock;
+  std::vector<uint64_t> part(nblocks ? nblocks : 1, 0);
+  std::atomic<size_t> next(0);
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= nblocks) return;
+      const unsigned char* b = (const unsigned char*)ptr + i * kBlock;
+      const size_t len = (i + 1 == nblocks) ? bytes - i * kBlock : kBlock;
+      uint64_t hh[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+      size_t o = 0;
+      for (; o + 32 <= len; o += 32) {
+        uint64_t w[4];
+        std::memcpy(w, b + o, 32);
+        for (int k = 0; k < 4; ++k) { hh[k] = (hh[k] ^ w[k]) * 0x100000001B3ull; hh[k] ^= hh[k] >> 29; }
+      }
+      uint64_t tail = 0;
+      for (; o < len; ++o) tail = tail * 131 + b[o];
+      uint64_t r = tail ^ (uint64_t)len;
+      for (int k = 0; k < 4; ++k) r = (r ^ hh[k]) * 0x9E3779B97F4A7C15ull + (r >> 31);
+      part[i] = r;
+    }
+  };
+  unsigned hc = std::thread::hardware_concurrency();
+  int nw = (int)(hc ? (hc + 1) / 2 : 4);
+  if (nw > 8) nw = 8;
+  if ((size_t)nw > nblocks) nw = (int)(nblocks ? nblocks : 1);
+  std::vector<std::thread> pool;
+  for (int w = 1; w < nw; ++w) { try { pool.emplace_back(work); } catch (...) { break; } }
+  work();
+  for (auto& t : pool) t.join();
+  uint64_t r = 0x84222325CBF29CE4ull ^ (uint64_t)bytes;
+  for (size_t i = 0; i < nblocks; ++i) r = (r ^ part[i]) * 0x100000001B3ull + (r >> 33);
+  return r;
+}
+size_t cond_elem_bytes(gpv_cond_type t) { return t == GPV_COND_F64 ? 8 : (t == GPV_COND_RLOGICAL_I32 ? 4 : 1); }
+}  // namespace
+
+extern "C" void gpv_release_cached(void) {
+  std::lock_guard<std::mutex> lk(g_stateless.mu);
+  if (g_stateless.h) { gpv_destroy(g_stateless.h); g_stateless.h = nullptr; }
+}
+
 extern "C" gpv_status gpv_U_NZentries(int Ncores, int64_t n, int64_t Nlocs, int p, int d,
                                       const double* locs, const int32_t* revNNarray,
                                       const void* revCond, gpv_cond_type cond_type,
@@ -1728,11 +1790,34 @@ extern "C" gpv_status gpv_U_NZentries(int Ncores, int64_t n, int64_t Nlocs, int 
   // validate covType before touching the device, like the message at U_NZentries.cpp:27-29
   CovSetup probe;
   gpv_status s = setup_cov(covType, covparms, ncov, 1.0, &probe); if (s) return s;
-  gpv_handle* h = nullptr;
-  s = gpv_create(&h, Nlocs, p, d, locs, revNNarray, revCond, cond_type, nullptr, 0, Nlocs, device);
-  if (s) return s;
-  s = gpv_u_nzentries(h, covType, covparms, ncov, nuggets, nuggets_obsord, n, Lentries, Zentries, nfail, first_fail);
-  gpv_destroy(h);
+  if (!locs || !revNNarray || !revCond || Nlocs <= 0 || p <= 0 || d <= 0) return fail(GPV_ERR_ARG, "gpv_U_NZentries: null or empty argument");
+  const char* env = std::getenv("GPV_STATELESS_CACHE");
+  if (env && env[0] == '0') {
+    gpv_handle* h = nullptr;
+    s = gpv_create(&h, Nlocs, p, d, locs, revNNarray, revCond, cond_type, nullptr, 0, Nlocs, device);
+    if (s) return s;
+    s = gpv_u_nzentries(h, covType, covparms, ncov, nuggets, nuggets_obsord, n, Lentries, Zentries, nfail, first_fail);
+    gpv_destroy(h);
+    return s;
+  }
+  StatelessCache& c = g_stateless;
+  std::lock_guard<std::mutex> lk(c.mu);
+  const uint64_t ks = fingerprint(locs, sizeof(double) * (size_t)Nlocs * d) * 31 +
+                      fingerprint(revNNarray, sizeof(int32_t) * (size_t)Nlocs * p);
+  const uint64_t kc = fingerprint(revCond, cond_elem_bytes(cond_type) * (size_t)Nlocs * p);
+  const bool same = c.h && c.Nlocs == Nlocs && c.p == p && c.d == d && c.device == device && c.key_static == ks;
+  if (!same) {
+    if (c.h) { gpv_destroy(c.h); c.h = nullptr; }
+    s = gpv_create(&c.h, Nlocs, p, d, locs, revNNarray, revCond, cond_type, nullptr, 0, Nlocs, device);
+    if (s) { c.h = nullptr; return s; }
+    c.Nlocs = Nlocs; c.p = p; c.d = d; c.device = device; c.key_static = ks; c.key_cond = kc; c.cond_type = (int)cond_type;
+  } else if (c.key_cond != kc || c.cond_type != (int)cond_type) {
+    s = gpv_set_revcond(c.h, revCond, cond_type);
+    if (s) { gpv_destroy(c.h); c.h = nullptr; return s; }
+    c.key_cond = kc; c.cond_type = (int)cond_type;
+  }
+  s = gpv_u_nzentries(c.h, covType, covparms, ncov, nuggets, nuggets_obsord, n, Lentries, Zentries, nfail, first_fail);
+  if (s) { gpv_destroy(c.h); c.h = nullptr; }               // do not keep a handle a call failed on
   return s;
 }
 

@@ -270,6 +270,10 @@ gpv_status gpv_U_NZentries(int Ncores, int64_t n, int64_t Nlocs, int p, int d, c
                            const double* nuggets_obsord, const char* covType,
                            const double* covparms, int ncovparms, double* Lentries,
                            double* Zentries, int64_t* nfail, int64_t* first_fail, int device);
+/* gpv_U_NZentries keeps the handle of its last call and recognises the next call's locs / revNNarray by a 64-bit
+ * fingerprint (a different revCond alone is re-uploaded; GPV_STATELESS_CACHE=0: create and destroy per call).
+ * This frees the kept handle and its device memory (package unload). */
+void gpv_release_cached(void);
 
 /* ---- covariance functions alone (MaternFun / EsqeFun, exported by the reference:
  * R/RcppExports.R:4-17, src/Matern.cpp:24, src/Esqe.cpp:17).  dist/out: len doubles on host. */

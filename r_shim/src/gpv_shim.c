@@ -404,6 +404,13 @@ static const R_CallMethodDef CallEntries[] = {
     {"_GPvecchia_createUcpp", (DL_FUNC)&gpvb200_createUcpp, 4},
     {NULL, NULL, 0}};
 
+void R_unload_GPvecchiaB200(DllInfo* dll) {
+  (void)dll;
+  gpv_release_cached();                       /* the handle the stateless U_NZentries route keeps between calls */
+  for (int i = 0; i < kPinPool; ++i)
+    if (pin_pool[i].p && !pin_pool[i].used) { gpv_host_free(pin_pool[i].p); pin_pool[i].p = NULL; pin_pool[i].cap = 0; }
+}
+
 void R_init_GPvecchiaB200(DllInfo* dll) {
   R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
   R_useDynamicSymbols(dll, FALSE);

@@ -718,6 +718,41 @@ def test_results_into_pageable_memory_go_through_the_copy_workers(layout):
         assert not np.any(r["Lentries"][~keep])
 
 
+def test_stateless_entry_point_recognises_unchanged_inputs_and_changed_ones(monkeypatch):
+    # gpv_U_NZentries keeps the handle of its last call (createU calls it hundreds of times with the same locsord /
+    # revNNarray) and recognises the arrays by a fingerprint of their CONTENT: an array changed in place, or another
+    # revCond alone, must show in the result
+    n, m = 3000, 9
+    va = _problem(n, m, 2, "SGV", stream=94)
+    prep = va["U_prep"]
+    nug = H.make_nuggets(n, stream=94)
+    cp = [1.1, H.default_range(n, 2), 1.5]
+    tol = 1e-8        # SGV blocks condition on the latent field (cond ~ 1e5): this test is about the cache
+    call = lambda nnarr, cond: G.U_NZentries(1, n, va["locsord"], nnarr, cond, nug, nug, "matern", cp)
+    ref = lambda nnarr, cond: O.U_NZentries(O.max_threads(), n, va["locsord"], nnarr, _rc_double(cond), nug, nug, "matern",
+                                            np.asarray(cp, float))
+    a, b = call(prep["revNNarray"], prep["revCond"]), call(prep["revNNarray"], prep["revCond"])     # second call: cache hit
+    assert np.array_equal(a["Lentries"], b["Lentries"]) and np.array_equal(a["Zentries"], b["Zentries"])
+    assert _rowscaled_err(a["Lentries"], ref(prep["revNNarray"], prep["revCond"])["Lentries"]) < tol
+    cond2 = prep["revCond"].copy()
+    cond2[prep["revNNarray"] != 0] = 0                                       # same neighbours, all conditioned on z
+    c = call(prep["revNNarray"], cond2)
+    assert not np.array_equal(c["Lentries"], a["Lentries"])
+    assert _rowscaled_err(c["Lentries"], ref(prep["revNNarray"], cond2)["Lentries"]) < tol
+    nn2 = prep["revNNarray"].copy()
+    rows = np.arange(n // 2, n, 7)
+    nn2[rows, 0] = 0                                                         # drop the farthest neighbour of some rows
+    d = call(nn2, cond2)
+    assert _rowscaled_err(d["Lentries"], ref(nn2, cond2)["Lentries"]) < tol
+    assert np.all(d["Lentries"][rows, -1] == 0) and np.all(c["Lentries"][rows, -1] != 0)
+    e = call(prep["revNNarray"], prep["revCond"])                            # and back
+    assert np.array_equal(e["Lentries"], a["Lentries"])
+    monkeypatch.setenv("GPV_STATELESS_CACHE", "0")
+    f = call(prep["revNNarray"], prep["revCond"])
+    assert np.array_equal(f["Lentries"], a["Lentries"])
+    G.lib.gpv_release_cached()
+
+
 def test_whole_loglik_on_gpu_for_pure_z_conditioning():
     # standard Vecchia: denominator terms are per-row closed forms (gpv_loglik_z)
     n, m = 3000, 20
